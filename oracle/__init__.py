@@ -138,7 +138,7 @@ class Oracle(_Lib):
                                          C.c_size_t, _u8p, C.c_size_t, _u64p]
         L.orc_chunked_decode.restype = C.c_long
         L.orc_chunked_decode.argtypes = [C.c_int, _u8p, C.c_size_t, _u64p, _u32p, _u32p, C.c_uint32, C.c_uint32,
-                                         C.c_size_t, _u8p, C.c_size_t]
+                                         C.c_size_t, C.c_size_t, _u8p, C.c_size_t]
         L.orc_alias_build.restype = C.c_int
         L.orc_alias_build.argtypes = [_u32p, _u32p, C.c_void_p, _u32p]
 
@@ -157,7 +157,7 @@ class Oracle(_Lib):
     def chunked_encode(self, coder, data, freqs, cum, chunk_syms, nlanes=32, scale_bits=12, align=16):
         data = _u8(data)
         n_chunks = (data.size + chunk_syms - 1) // chunk_syms
-        cap = 2 * data.size + n_chunks * (8 * nlanes + align + 64) + 64
+        cap = 2 * data.size + n_chunks * (8 * nlanes + 2 * align + 64) + 64
         blob = np.zeros(cap, np.uint8)
         offs = np.zeros(n_chunks + 1, np.uint64)
         r = self.lib.orc_chunked_encode(coder, _p(data, _u8p), data.size, _p(freqs, _u32p), _p(cum, _u32p), scale_bits,
@@ -166,12 +166,12 @@ class Oracle(_Lib):
             raise ValueError(f"chunked_encode rc={r}")
         return blob[:r].copy(), offs
 
-    def chunked_decode(self, coder, blob, offsets, n, freqs, cum, chunk_syms, nlanes=32, scale_bits=12):
+    def chunked_decode(self, coder, blob, offsets, n, freqs, cum, chunk_syms, nlanes=32, scale_bits=12, align=16):
         blob = _u8(blob)
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         out = np.zeros(max(n, 1), np.uint8)
         r = self.lib.orc_chunked_decode(coder, _p(blob, _u8p), blob.size, _p(offsets, _u64p), _p(freqs, _u32p),
-                                        _p(cum, _u32p), scale_bits, nlanes, chunk_syms, _p(out, _u8p), n)
+                                        _p(cum, _u32p), scale_bits, nlanes, chunk_syms, align, _p(out, _u8p), n)
         if r < 0:
             raise ValueError(f"chunked_decode rc={r}")
         return out[:n].copy()

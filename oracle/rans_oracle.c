@@ -596,12 +596,14 @@ done:
 }
 
 /* ------------------------------------------------------------------------ */
-/* Chunked container used by the GPU path (DESIGN.md "HBM layout"):          */
-/* the symbol buffer is cut into chunks of chunk_syms symbols; every chunk is */
-/* an independent nlanes-way stream exactly as produced by the *_encode       */
-/* functions above; chunk c's stream starts at blob + offsets[c], offsets are */
-/* rounded up to `align` bytes, offsets[n_chunks] = end of the last stream.   */
-/* coder: 0 = word (scale 12), 1 = byte/cum2sym, 2 = alias, 3 = rans64.       */
+/* Chunked container used by the GPU path (mirrors the    */
+/* statement in include/rans_b200.h): the symbol buffer is cut into chunks of */
+/* chunk_syms symbols; every chunk is an independent nlanes-way stream exactly */
+/* as produced by the *_encode functions above.  Streams are END-aligned:      */
+/* stream c occupies blob[offsets[c] .. E_c) with E_c = E_{c-1} +              */
+/* round_up(size_c, align), E_{-1} = 0; the gap in front of it is zero;        */
+/* offsets[n_chunks] = E_last.  coder: 0 = word (scale 12), 1 = byte/cum2sym,  */
+/* 2 = alias, 3 = rans64.                                                      */
 /* ------------------------------------------------------------------------ */
 
 static long one_encode(int coder, const uint8_t *in, size_t n, const uint32_t *freqs,
@@ -636,39 +638,48 @@ long orc_chunked_encode(int coder, const uint8_t *in, size_t n,
     if (chunk_syms == 0 || align == 0)
         return ORC_E_ARG;
     size_t n_chunks = (n + chunk_syms - 1) / chunk_syms;
-    size_t pos = 0;
+    size_t tmp_cap = 2 * chunk_syms + 8 * (size_t)nlanes + 64;
+    uint8_t *tmp = (uint8_t *)malloc(tmp_cap);
+    if (!tmp) return ORC_E_SPACE;
+    size_t end_prev = 0;
+    long rv = 0;
     for (size_t c = 0; c < n_chunks; c++) {
         size_t lo = c * chunk_syms;
         size_t m = (n - lo < chunk_syms) ? n - lo : chunk_syms;
-        pos = (pos + align - 1) / align * align;
-        if (pos > cap) return ORC_E_SPACE;
-        offsets[c] = pos;
-        long r = one_encode(coder, in + lo, m, freqs, cum, scale_bits, nlanes, blob + pos, cap - pos);
-        if (r < 0) return r;
-        pos += (size_t)r;
+        long r = one_encode(coder, in + lo, m, freqs, cum, scale_bits, nlanes, tmp, tmp_cap);
+        if (r < 0) { rv = r; goto done; }
+        size_t padded = ((size_t)r + align - 1) / align * align;
+        size_t end = end_prev + padded;
+        if (end > cap) { rv = ORC_E_SPACE; goto done; }
+        offsets[c] = end - (size_t)r;
+        memset(blob + end_prev, 0, padded - (size_t)r);
+        memcpy(blob + offsets[c], tmp, (size_t)r);
+        end_prev = end;
     }
-    offsets[n_chunks] = pos;
-    return (long)pos;
+    offsets[n_chunks] = end_prev;
+    rv = (long)end_prev;
+done:
+    free(tmp);
+    return rv;
 }
 
-/* stream c occupies [offsets[c], offsets[c] + sizes[c]); sizes may be NULL, in
- * which case the extent is taken up to the next (aligned) offset, which is
- * legal because decoders never read past what they need. */
 long orc_chunked_decode(int coder, const uint8_t *blob, size_t blob_size, const uint64_t *offsets,
                         const uint32_t freqs[256], const uint32_t cum[257],
-                        uint32_t scale_bits, uint32_t nlanes, size_t chunk_syms,
+                        uint32_t scale_bits, uint32_t nlanes, size_t chunk_syms, size_t align,
                         uint8_t *out, size_t n)
 {
-    if (chunk_syms == 0)
+    if (chunk_syms == 0 || align == 0)
         return ORC_E_ARG;
     size_t n_chunks = (n + chunk_syms - 1) / chunk_syms;
     for (size_t c = 0; c < n_chunks; c++) {
         size_t lo = c * chunk_syms;
         size_t m = (n - lo < chunk_syms) ? n - lo : chunk_syms;
-        if (offsets[c + 1] > blob_size || offsets[c] > offsets[c + 1]) return ORC_E_STREAM;
-        long r = one_decode(coder, blob + offsets[c], (size_t)(offsets[c + 1] - offsets[c]),
+        uint64_t end = offsets[c + 1] / align * align;
+        if (end > blob_size || offsets[c] > end) return ORC_E_STREAM;
+        long r = one_decode(coder, blob + offsets[c], (size_t)(end - offsets[c]),
                             freqs, cum, scale_bits, nlanes, out + lo, m);
         if (r < 0) return r;
+        if ((uint64_t)r != end - offsets[c]) return ORC_E_STREAM;   /* must end exactly at E_c */
     }
     return (long)n;
 }

@@ -1,0 +1,608 @@
+// rans_b200.cu -- C-ABI (include/rans_b200.h) over the sm_100a rANS kernels.
+//
+// Host code is C++ like the reference's drivers; it owns no global state: everything
+// lives in rb200_ctx (device, stream, grow-only workspaces) and rb200_model (device
+// tables).  Data pointers are either host memory (the call stages them through the
+// context's device buffers and is synchronous, like the reference's loops) or device
+// memory (the call only enqueues kernels on the context's stream).
+#include "rans_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "alias_kernels.cuh"
+#include "block_kernels.cuh"
+#include "tables.h"
+#include "word_kernels.cuh"
+
+using namespace rb200;
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct rb200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint32_t* d_status = nullptr;     // kStat* bits, OR-ed by kernels
+    uint32_t* h_status = nullptr;     // pinned mirror
+    uint64_t launches = 0;
+    std::string last_error;
+    // encode workspaces
+    DevBuf scratch, sizes;
+    // staging for RB200_MEM_HOST calls
+    DevBuf st_in, st_blob, st_offsets, st_out, st_aux;
+};
+
+struct rb200_model {
+    rb200_ctx* ctx = nullptr;
+    int coder = 0;
+    uint32_t scale_bits = 0;
+    int wide = 0;
+    uint32_t* d_word_dec = nullptr;          // 4096 x u32
+    WordEncEntry* d_word_enc = nullptr;      // 256
+    uint32_t* d_alias_divider = nullptr;     // 256
+    AliasDecEntry* d_alias_dec = nullptr;    // 512
+    AliasEncEntry* d_alias_enc = nullptr;    // 256
+    uint16_t* d_alias_remap = nullptr;       // 1 << scale_bits
+};
+
+namespace {
+
+int cuda_fail(rb200_ctx* ctx, cudaError_t e, const char* what)
+{
+    if (ctx) ctx->last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return RB200_E_CUDA;
+}
+
+#define RB_CUDA(ctx, call)                                              \
+    do {                                                                \
+        cudaError_t e_ = (call);                                        \
+        if (e_ != cudaSuccess) return cuda_fail((ctx), e_, #call);      \
+    } while (0)
+
+int reserve(rb200_ctx* ctx, DevBuf& b, size_t bytes)
+{
+    if (bytes <= b.cap) return RB200_OK;
+    if (b.p) {
+        RB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        RB_CUDA(ctx, cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        b.p = nullptr;
+        cuda_fail(ctx, e, "cudaMalloc(workspace)");
+        return RB200_E_NOMEM;
+    }
+    b.cap = want;
+    return RB200_OK;
+}
+
+void release(DevBuf& b)
+{
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+inline size_t round16(size_t v) { return (v + 15) & ~static_cast<size_t>(15); }
+inline uint32_t slot_bytes_for(uint32_t chunk_syms) { return static_cast<uint32_t>(round16(kHeaderBytes + 2ull * chunk_syms)); }
+
+int status_to_code(uint32_t bits)
+{
+    if (bits & kStatSymbol) return RB200_E_SYMBOL;
+    if (bits & kStatSpace) return RB200_E_SPACE;
+    if (bits & kStatStream) return RB200_E_STREAM;
+    return RB200_OK;
+}
+
+int check_launch(rb200_ctx* ctx, const char* what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(ctx, e, what);
+    ctx->launches++;
+    return RB200_OK;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev)
+    {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+constexpr uint32_t kMinChunk = 32;
+constexpr uint32_t kMaxChunk = 1u << 24;
+
+bool chunk_ok(uint32_t chunk_syms) { return chunk_syms >= kMinChunk && chunk_syms <= kMaxChunk; }
+
+}  // namespace
+
+extern "C" int rb200_version(void) { return RB200_VERSION; }
+
+extern "C" const char* rb200_strerror(int code)
+{
+    switch (code) {
+    case RB200_OK: return "ok";
+    case RB200_E_ARG: return "bad argument";
+    case RB200_E_MODEL: return "invalid model";
+    case RB200_E_SPACE: return "output buffer too small";
+    case RB200_E_STREAM: return "corrupt or truncated stream";
+    case RB200_E_CUDA: return "CUDA error";
+    case RB200_E_NOMEM: return "out of device memory";
+    case RB200_E_SYMBOL: return "symbol with zero model frequency";
+    }
+    return "unknown";
+}
+
+extern "C" int rb200_ctx_create(rb200_ctx** out, int device, void* stream)
+{
+    if (!out) return RB200_E_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return RB200_E_CUDA;
+    rb200_ctx* ctx = new (std::nothrow) rb200_ctx;
+    if (!ctx) return RB200_E_NOMEM;
+    ctx->device = device;
+    ctx->stream = static_cast<cudaStream_t>(stream);
+    DeviceGuard g(device);
+    cudaError_t e = cudaMalloc(&ctx->d_status, sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemset(ctx->d_status, 0, sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_status, sizeof(uint32_t));
+    if (e != cudaSuccess) {
+        if (ctx->d_status) cudaFree(ctx->d_status);
+        delete ctx;
+        return RB200_E_CUDA;
+    }
+    *ctx->h_status = 0;
+    // the decoders want the large shared-memory carve-out (tables + per-warp rings)
+    cudaFuncSetAttribute(word_decode_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(word_decode_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(word_encode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    configure_alias_kernels();
+    configure_block_kernels();
+    cudaGetLastError();
+    *out = ctx;
+    return RB200_OK;
+}
+
+extern "C" void rb200_ctx_destroy(rb200_ctx* ctx)
+{
+    if (!ctx) return;
+    DeviceGuard g(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    release(ctx->scratch); release(ctx->sizes);
+    release(ctx->st_in); release(ctx->st_blob); release(ctx->st_offsets); release(ctx->st_out); release(ctx->st_aux);
+    if (ctx->d_status) cudaFree(ctx->d_status);
+    if (ctx->h_status) cudaFreeHost(ctx->h_status);
+    delete ctx;
+}
+
+extern "C" int rb200_ctx_set_stream(rb200_ctx* ctx, void* stream)
+{
+    if (!ctx) return RB200_E_ARG;
+    ctx->stream = static_cast<cudaStream_t>(stream);
+    return RB200_OK;
+}
+
+extern "C" const char* rb200_last_cuda_error(const rb200_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+extern "C" uint64_t rb200_launch_count(const rb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int rb200_sync(rb200_ctx* ctx)
+{
+    if (!ctx) return RB200_E_ARG;
+    DeviceGuard g(ctx->device);
+    RB_CUDA(ctx, cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    RB_CUDA(ctx, cudaMemsetAsync(ctx->d_status, 0, sizeof(uint32_t), ctx->stream));
+    RB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return status_to_code(*ctx->h_status);
+}
+
+// ---------------------------------------------------------------------------
+// models
+// ---------------------------------------------------------------------------
+
+extern "C" void rb200_model_destroy(rb200_model* m)
+{
+    if (!m) return;
+    DeviceGuard g(m->ctx->device);
+    cudaStreamSynchronize(m->ctx->stream);
+    cudaFree(m->d_word_dec); cudaFree(m->d_word_enc);
+    cudaFree(m->d_alias_divider); cudaFree(m->d_alias_dec); cudaFree(m->d_alias_enc); cudaFree(m->d_alias_remap);
+    delete m;
+}
+
+extern "C" int rb200_model_create(rb200_ctx* ctx, int coder, uint32_t scale_bits, const uint32_t freqs[256], rb200_model** out)
+{
+    if (!ctx || !freqs || !out) return RB200_E_ARG;
+    *out = nullptr;
+    DeviceGuard g(ctx->device);
+    rb200_model* m = new (std::nothrow) rb200_model;
+    if (!m) return RB200_E_NOMEM;
+    m->ctx = ctx;
+    m->coder = coder;
+    m->scale_bits = scale_bits;
+    int rc = RB200_OK;
+    cudaError_t e = cudaSuccess;
+    if (coder == RB200_CODER_WORD) {
+        if (scale_bits != kWordScaleBits) { delete m; return RB200_E_ARG; }
+        WordDeviceTables* t = new (std::nothrow) WordDeviceTables;
+        if (!t) { delete m; return RB200_E_NOMEM; }
+        rc = build_word_device_tables(freqs, *t);
+        if (rc == RB200_OK) {
+            m->wide = t->wide;
+            e = cudaMalloc(&m->d_word_dec, sizeof t->dec);
+            if (e == cudaSuccess) e = cudaMalloc(&m->d_word_enc, sizeof t->enc);
+            if (e == cudaSuccess) e = cudaMemcpy(m->d_word_dec, t->dec, sizeof t->dec, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(m->d_word_enc, t->enc, sizeof t->enc, cudaMemcpyHostToDevice);
+        }
+        delete t;
+    } else if (coder == RB200_CODER_ALIAS) {
+        AliasDeviceTables* t = new (std::nothrow) AliasDeviceTables;
+        if (!t) { delete m; return RB200_E_NOMEM; }
+        rc = build_alias_device_tables(freqs, scale_bits, *t);
+        if (rc == RB200_OK) {
+            const size_t remap_bytes = t->remap.size() * sizeof(uint16_t);
+            e = cudaMalloc(&m->d_alias_divider, sizeof t->divider);
+            if (e == cudaSuccess) e = cudaMalloc(&m->d_alias_dec, sizeof t->dec);
+            if (e == cudaSuccess) e = cudaMalloc(&m->d_alias_enc, sizeof t->enc);
+            if (e == cudaSuccess) e = cudaMalloc(&m->d_alias_remap, remap_bytes);
+            if (e == cudaSuccess) e = cudaMemcpy(m->d_alias_divider, t->divider, sizeof t->divider, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(m->d_alias_dec, t->dec, sizeof t->dec, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(m->d_alias_enc, t->enc, sizeof t->enc, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(m->d_alias_remap, t->remap.data(), remap_bytes, cudaMemcpyHostToDevice);
+        }
+        delete t;
+    } else {
+        delete m;
+        return RB200_E_ARG;
+    }
+    if (rc != RB200_OK || e != cudaSuccess) {
+        if (e != cudaSuccess) rc = cuda_fail(ctx, e, "model upload");
+        rb200_model_destroy(m);
+        return rc;
+    }
+    *out = m;
+    return RB200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// geometry
+// ---------------------------------------------------------------------------
+
+extern "C" size_t rb200_chunk_count(size_t n, uint32_t chunk_syms)
+{
+    if (!chunk_syms) return 0;
+    return (n + chunk_syms - 1) / chunk_syms;
+}
+
+// every renormalisation emits at most 2 bytes per symbol (word coder: <= one u16,
+// rans_word_sse41.h:85-89; byte coder at scale_bits >= 8: state < 2^31 and
+// x_max >= 2^15 -> <= two bytes, rans_byte.h:64-70), plus the 128-byte header,
+// each stream padded to a multiple of 16.
+extern "C" size_t rb200_encode_bound(size_t n, uint32_t chunk_syms)
+{
+    if (!chunk_syms) return 0;
+    const size_t full = n / chunk_syms, tail = n % chunk_syms;
+    size_t b = full * round16(kHeaderBytes + 2ull * chunk_syms);
+    if (tail) b += round16(kHeaderBytes + 2ull * tail);
+    return b;
+}
+
+// ---------------------------------------------------------------------------
+// device-resident hot path
+// ---------------------------------------------------------------------------
+
+namespace {
+
+int encode_device(rb200_ctx* ctx, const rb200_model* model, const uint8_t* d_in, size_t n, uint32_t chunk_syms,
+                  uint8_t* d_blob, size_t blob_cap, uint64_t* d_offsets)
+{
+    const size_t n_chunks_sz = rb200_chunk_count(n, chunk_syms);
+    if (n_chunks_sz >= (1ull << 31)) return RB200_E_ARG;
+    const uint32_t n_chunks = static_cast<uint32_t>(n_chunks_sz);
+    const uint32_t slot = slot_bytes_for(chunk_syms);
+    int rc = reserve(ctx, ctx->scratch, static_cast<size_t>(n_chunks) * slot + 16);
+    if (rc != RB200_OK) return rc;
+    rc = reserve(ctx, ctx->sizes, (static_cast<size_t>(n_chunks) + 1) * sizeof(uint32_t));
+    if (rc != RB200_OK) return rc;
+    uint8_t* scratch = static_cast<uint8_t*>(ctx->scratch.p);
+    uint32_t* sizes = static_cast<uint32_t*>(ctx->sizes.p);
+    if (n_chunks) {
+        if (model->coder == RB200_CODER_WORD) {
+            const uint32_t grid = (n_chunks + kEncWarps - 1) / kEncWarps;
+            word_encode_kernel<<<grid, kEncWarps * 32, 0, ctx->stream>>>(d_in, n, chunk_syms, n_chunks, model->d_word_enc,
+                                                                          scratch, slot, sizes, ctx->d_status);
+            rc = check_launch(ctx, "word_encode_kernel");
+        } else {
+            rc = launch_alias_encode(ctx->stream, d_in, n, chunk_syms, n_chunks, model->scale_bits, model->d_alias_enc,
+                                     model->d_alias_remap, scratch, slot, sizes, ctx->d_status);
+            if (rc == RB200_OK) rc = check_launch(ctx, "alias_encode_kernel");
+        }
+        if (rc != RB200_OK) return rc;
+    }
+    directory_scan_kernel<<<1, 1024, 0, ctx->stream>>>(sizes, n_chunks, d_offsets, blob_cap, ctx->d_status);
+    rc = check_launch(ctx, "directory_scan_kernel");
+    if (rc != RB200_OK) return rc;
+    if (n_chunks) {
+        const uint32_t grid = (n_chunks + kCopyWarps - 1) / kCopyWarps;
+        compact_kernel<<<grid, kCopyWarps * 32, 0, ctx->stream>>>(scratch, slot, sizes, d_offsets, n_chunks, d_blob, blob_cap);
+        rc = check_launch(ctx, "compact_kernel");
+    }
+    return rc;
+}
+
+int decode_device(rb200_ctx* ctx, const rb200_model* model, const uint8_t* d_blob, size_t blob_size, const uint64_t* d_offsets,
+                  uint32_t chunk_syms, uint8_t* d_out, size_t n)
+{
+    const size_t n_chunks_sz = rb200_chunk_count(n, chunk_syms);
+    if (n_chunks_sz >= (1ull << 31)) return RB200_E_ARG;
+    const uint32_t n_chunks = static_cast<uint32_t>(n_chunks_sz);
+    if (!n_chunks) return RB200_OK;
+    if (model->coder == RB200_CODER_WORD) {
+        const uint32_t grid = (n_chunks + kDecWarps - 1) / kDecWarps;
+        if (model->wide)
+            word_decode_kernel<true><<<grid, kDecWarps * 32, 0, ctx->stream>>>(d_blob, blob_size, d_offsets, model->d_word_dec, d_out,
+                                                                                n, chunk_syms, n_chunks, ctx->d_status);
+        else
+            word_decode_kernel<false><<<grid, kDecWarps * 32, 0, ctx->stream>>>(d_blob, blob_size, d_offsets, model->d_word_dec, d_out,
+                                                                                 n, chunk_syms, n_chunks, ctx->d_status);
+        return check_launch(ctx, "word_decode_kernel");
+    }
+    int rc = launch_alias_decode(ctx->stream, d_blob, blob_size, d_offsets, model->scale_bits, model->d_alias_divider,
+                                 model->d_alias_dec, d_out, n, chunk_syms, n_chunks, ctx->d_status);
+    if (rc == RB200_OK) rc = check_launch(ctx, "alias_decode_kernel");
+    return rc;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+extern "C" int rb200_encode(rb200_ctx* ctx, const rb200_model* model, const uint8_t* in, size_t n, uint32_t chunk_syms,
+                            uint8_t* blob, size_t blob_cap, uint64_t* offsets, size_t* blob_size, int mem_kind)
+{
+    if (!ctx || !model || model->ctx != ctx || !blob || !offsets || (!in && n) || !chunk_ok(chunk_syms)) return RB200_E_ARG;
+    DeviceGuard g(ctx->device);
+    const size_t n_chunks = rb200_chunk_count(n, chunk_syms);
+    if (mem_kind == RB200_MEM_DEVICE) {
+        if (!aligned16(blob) || (reinterpret_cast<uintptr_t>(offsets) & 7)) return RB200_E_ARG;
+        return encode_device(ctx, model, in, n, chunk_syms, blob, blob_cap, offsets);
+    }
+    if (mem_kind != RB200_MEM_HOST) return RB200_E_ARG;
+    // host buffers: stage in, run, stage out; synchronous like the reference's loops
+    const size_t bound = rb200_encode_bound(n, chunk_syms);
+    const size_t dev_cap = bound < blob_cap ? bound : round16(blob_cap) > blob_cap ? blob_cap & ~static_cast<size_t>(15) : blob_cap;
+    int rc = reserve(ctx, ctx->st_in, n + 16);
+    if (rc == RB200_OK) rc = reserve(ctx, ctx->st_blob, bound + 16);
+    if (rc == RB200_OK) rc = reserve(ctx, ctx->st_offsets, (n_chunks + 1) * sizeof(uint64_t));
+    if (rc != RB200_OK) return rc;
+    uint8_t* d_in = static_cast<uint8_t*>(ctx->st_in.p);
+    uint8_t* d_blob = static_cast<uint8_t*>(ctx->st_blob.p);
+    uint64_t* d_off = static_cast<uint64_t*>(ctx->st_offsets.p);
+    if (n) RB_CUDA(ctx, cudaMemcpyAsync(d_in, in, n, cudaMemcpyHostToDevice, ctx->stream));
+    rc = encode_device(ctx, model, d_in, n, chunk_syms, d_blob, dev_cap, d_off);
+    if (rc != RB200_OK) return rc;
+    RB_CUDA(ctx, cudaMemcpyAsync(offsets, d_off, (n_chunks + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    rc = rb200_sync(ctx);
+    if (rc != RB200_OK) return rc;
+    const size_t total = static_cast<size_t>(offsets[n_chunks]);
+    if (total > blob_cap) return RB200_E_SPACE;
+    if (total) RB_CUDA(ctx, cudaMemcpyAsync(blob, d_blob, total, cudaMemcpyDeviceToHost, ctx->stream));
+    RB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (blob_size) *blob_size = total;
+    return RB200_OK;
+}
+
+extern "C" int rb200_decode(rb200_ctx* ctx, const rb200_model* model, const uint8_t* blob, size_t blob_size,
+                            const uint64_t* offsets, uint32_t chunk_syms, uint8_t* out, size_t n, int mem_kind)
+{
+    if (!ctx || !model || model->ctx != ctx || !offsets || (!out && n) || (!blob && blob_size) || !chunk_ok(chunk_syms))
+        return RB200_E_ARG;
+    if (blob_size & 15) return RB200_E_ARG;     // container invariant: the blob ends on a 16-byte boundary
+    DeviceGuard g(ctx->device);
+    const size_t n_chunks = rb200_chunk_count(n, chunk_syms);
+    if (mem_kind == RB200_MEM_DEVICE) {
+        if (!aligned16(blob) || (reinterpret_cast<uintptr_t>(offsets) & 7)) return RB200_E_ARG;
+        return decode_device(ctx, model, blob, blob_size, offsets, chunk_syms, out, n);
+    }
+    if (mem_kind != RB200_MEM_HOST) return RB200_E_ARG;
+    int rc = reserve(ctx, ctx->st_blob, blob_size + 16);
+    if (rc == RB200_OK) rc = reserve(ctx, ctx->st_offsets, (n_chunks + 1) * sizeof(uint64_t));
+    if (rc == RB200_OK) rc = reserve(ctx, ctx->st_out, n + 16);
+    if (rc != RB200_OK) return rc;
+    uint8_t* d_blob = static_cast<uint8_t*>(ctx->st_blob.p);
+    uint64_t* d_off = static_cast<uint64_t*>(ctx->st_offsets.p);
+    uint8_t* d_out = static_cast<uint8_t*>(ctx->st_out.p);
+    if (blob_size) RB_CUDA(ctx, cudaMemcpyAsync(d_blob, blob, blob_size, cudaMemcpyHostToDevice, ctx->stream));
+    RB_CUDA(ctx, cudaMemcpyAsync(d_off, offsets, (n_chunks + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    rc = decode_device(ctx, model, d_blob, blob_size, d_off, chunk_syms, d_out, n);
+    if (rc != RB200_OK) return rc;
+    if (n) RB_CUDA(ctx, cudaMemcpyAsync(out, d_out, n, cudaMemcpyDeviceToHost, ctx->stream));
+    return rb200_sync(ctx);
+}
+
+// ---------------------------------------------------------------------------
+// histogram + per-block models: block_kernels.cuh
+// ---------------------------------------------------------------------------
+
+extern "C" int rb200_histogram(rb200_ctx* ctx, const uint8_t* in, size_t n, uint64_t counts[256], int mem_kind)
+{
+    if (!ctx || !counts || (!in && n)) return RB200_E_ARG;
+    DeviceGuard g(ctx->device);
+    int rc = reserve(ctx, ctx->st_aux, 256 * sizeof(unsigned long long));
+    if (rc != RB200_OK) return rc;
+    const uint8_t* d_in = in;
+    if (mem_kind == RB200_MEM_HOST) {
+        rc = reserve(ctx, ctx->st_in, n + 16);
+        if (rc != RB200_OK) return rc;
+        if (n) RB_CUDA(ctx, cudaMemcpyAsync(ctx->st_in.p, in, n, cudaMemcpyHostToDevice, ctx->stream));
+        d_in = static_cast<const uint8_t*>(ctx->st_in.p);
+    } else if (mem_kind != RB200_MEM_DEVICE) {
+        return RB200_E_ARG;
+    }
+    unsigned long long* d_counts = static_cast<unsigned long long*>(ctx->st_aux.p);
+    RB_CUDA(ctx, cudaMemsetAsync(d_counts, 0, 256 * sizeof(unsigned long long), ctx->stream));
+    if (n) {
+        launch_histogram(ctx->stream, d_in, n, d_counts);
+        rc = check_launch(ctx, "histogram_kernel");
+        if (rc != RB200_OK) return rc;
+    }
+    RB_CUDA(ctx, cudaMemcpyAsync(counts, d_counts, 256 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    RB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RB200_OK;
+}
+
+extern "C" int rb200_blocks_build_models(rb200_ctx* ctx, const uint8_t* in, uint32_t n_blocks, uint32_t block_size,
+                                         uint16_t* block_freqs, int mem_kind)
+{
+    if (!ctx || !in || !block_freqs || !n_blocks || !block_size) return RB200_E_ARG;
+    DeviceGuard g(ctx->device);
+    const size_t n = static_cast<size_t>(n_blocks) * block_size;
+    const size_t fbytes = static_cast<size_t>(n_blocks) * 256 * sizeof(uint16_t);
+    const uint8_t* d_in = in;
+    uint16_t* d_freqs = block_freqs;
+    int rc;
+    if (mem_kind == RB200_MEM_HOST) {
+        rc = reserve(ctx, ctx->st_in, n + 16);
+        if (rc == RB200_OK) rc = reserve(ctx, ctx->st_aux, fbytes);
+        if (rc != RB200_OK) return rc;
+        RB_CUDA(ctx, cudaMemcpyAsync(ctx->st_in.p, in, n, cudaMemcpyHostToDevice, ctx->stream));
+        d_in = static_cast<const uint8_t*>(ctx->st_in.p);
+        d_freqs = static_cast<uint16_t*>(ctx->st_aux.p);
+    } else if (mem_kind != RB200_MEM_DEVICE) {
+        return RB200_E_ARG;
+    }
+    launch_block_models(ctx->stream, d_in, n_blocks, block_size, d_freqs, ctx->d_status);
+    rc = check_launch(ctx, "block_model_kernel");
+    if (rc != RB200_OK) return rc;
+    if (mem_kind == RB200_MEM_HOST) {
+        RB_CUDA(ctx, cudaMemcpyAsync(block_freqs, d_freqs, fbytes, cudaMemcpyDeviceToHost, ctx->stream));
+        return rb200_sync(ctx);
+    }
+    return RB200_OK;
+}
+
+namespace {
+
+int blocks_encode_device(rb200_ctx* ctx, const uint8_t* d_in, uint32_t n_blocks, uint32_t block_size, const uint16_t* d_freqs,
+                         uint32_t chunk_syms, uint8_t* d_blob, size_t blob_cap, uint64_t* d_offsets)
+{
+    const uint32_t per_block = block_size / chunk_syms;
+    const uint64_t n_chunks64 = static_cast<uint64_t>(n_blocks) * per_block;
+    if (n_chunks64 >= (1ull << 31)) return RB200_E_ARG;
+    const uint32_t n_chunks = static_cast<uint32_t>(n_chunks64);
+    const uint32_t slot = slot_bytes_for(chunk_syms);
+    int rc = reserve(ctx, ctx->scratch, static_cast<size_t>(n_chunks) * slot + 16);
+    if (rc == RB200_OK) rc = reserve(ctx, ctx->sizes, (static_cast<size_t>(n_chunks) + 1) * sizeof(uint32_t));
+    if (rc != RB200_OK) return rc;
+    uint8_t* scratch = static_cast<uint8_t*>(ctx->scratch.p);
+    uint32_t* sizes = static_cast<uint32_t*>(ctx->sizes.p);
+    launch_block_encode(ctx->stream, d_in, n_blocks, block_size, d_freqs, chunk_syms, scratch, slot, sizes, ctx->d_status);
+    rc = check_launch(ctx, "block_encode_kernel");
+    if (rc != RB200_OK) return rc;
+    directory_scan_kernel<<<1, 1024, 0, ctx->stream>>>(sizes, n_chunks, d_offsets, blob_cap, ctx->d_status);
+    rc = check_launch(ctx, "directory_scan_kernel");
+    if (rc != RB200_OK) return rc;
+    const uint32_t grid = (n_chunks + kCopyWarps - 1) / kCopyWarps;
+    compact_kernel<<<grid, kCopyWarps * 32, 0, ctx->stream>>>(scratch, slot, sizes, d_offsets, n_chunks, d_blob, blob_cap);
+    return check_launch(ctx, "compact_kernel");
+}
+
+bool blocks_geometry_ok(uint32_t n_blocks, uint32_t block_size, uint32_t chunk_syms)
+{
+    return n_blocks && block_size && chunk_ok(chunk_syms) && block_size % chunk_syms == 0 && block_size / chunk_syms <= 32;
+}
+
+}  // namespace
+
+extern "C" int rb200_blocks_encode(rb200_ctx* ctx, const uint8_t* in, uint32_t n_blocks, uint32_t block_size,
+                                   const uint16_t* block_freqs, uint32_t chunk_syms, uint8_t* blob, size_t blob_cap,
+                                   uint64_t* offsets, size_t* blob_size, int mem_kind)
+{
+    if (!ctx || !in || !block_freqs || !blob || !offsets || !blocks_geometry_ok(n_blocks, block_size, chunk_syms)) return RB200_E_ARG;
+    DeviceGuard g(ctx->device);
+    const size_t n = static_cast<size_t>(n_blocks) * block_size;
+    const size_t n_chunks = static_cast<size_t>(n_blocks) * (block_size / chunk_syms);
+    if (mem_kind == RB200_MEM_DEVICE) {
+        if (!aligned16(blob) || (reinterpret_cast<uintptr_t>(offsets) & 7)) return RB200_E_ARG;
+        return blocks_encode_device(ctx, in, n_blocks, block_size, block_freqs, chunk_syms, blob, blob_cap, offsets);
+    }
+    if (mem_kind != RB200_MEM_HOST) return RB200_E_ARG;
+    const size_t bound = rb200_encode_bound(n, chunk_syms);
+    const size_t fbytes = static_cast<size_t>(n_blocks) * 256 * sizeof(uint16_t);
+    int rc = reserve(ctx, ctx->st_in, n + 16);
+    if (rc == RB200_OK) rc = reserve(ctx, ctx->st_blob, bound + 16);
+    if (rc == RB200_OK) rc = reserve(ctx, ctx->st_offsets, (n_chunks + 1) * sizeof(uint64_t));
+    if (rc == RB200_OK) rc = reserve(ctx, ctx->st_aux, fbytes);
+    if (rc != RB200_OK) return rc;
+    RB_CUDA(ctx, cudaMemcpyAsync(ctx->st_in.p, in, n, cudaMemcpyHostToDevice, ctx->stream));
+    RB_CUDA(ctx, cudaMemcpyAsync(ctx->st_aux.p, block_freqs, fbytes, cudaMemcpyHostToDevice, ctx->stream));
+    uint64_t* d_off = static_cast<uint64_t*>(ctx->st_offsets.p);
+    rc = blocks_encode_device(ctx, static_cast<const uint8_t*>(ctx->st_in.p), n_blocks, block_size,
+                              static_cast<const uint16_t*>(ctx->st_aux.p), chunk_syms, static_cast<uint8_t*>(ctx->st_blob.p),
+                              bound, d_off);
+    if (rc != RB200_OK) return rc;
+    RB_CUDA(ctx, cudaMemcpyAsync(offsets, d_off, (n_chunks + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    rc = rb200_sync(ctx);
+    if (rc != RB200_OK) return rc;
+    const size_t total = static_cast<size_t>(offsets[n_chunks]);
+    if (total > blob_cap) return RB200_E_SPACE;
+    RB_CUDA(ctx, cudaMemcpyAsync(blob, ctx->st_blob.p, total, cudaMemcpyDeviceToHost, ctx->stream));
+    RB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (blob_size) *blob_size = total;
+    return RB200_OK;
+}
+
+extern "C" int rb200_blocks_decode(rb200_ctx* ctx, const uint8_t* blob, size_t blob_size, const uint64_t* offsets,
+                                   const uint16_t* block_freqs, uint32_t n_blocks, uint32_t block_size, uint32_t chunk_syms,
+                                   uint8_t* out, int mem_kind)
+{
+    if (!ctx || !blob || !offsets || !block_freqs || !out || !blocks_geometry_ok(n_blocks, block_size, chunk_syms)) return RB200_E_ARG;
+    if (blob_size & 15) return RB200_E_ARG;
+    DeviceGuard g(ctx->device);
+    const size_t n = static_cast<size_t>(n_blocks) * block_size;
+    const size_t n_chunks = static_cast<size_t>(n_blocks) * (block_size / chunk_syms);
+    if (n_chunks >= (1ull << 31)) return RB200_E_ARG;
+    if (mem_kind == RB200_MEM_DEVICE) {
+        if (!aligned16(blob) || (reinterpret_cast<uintptr_t>(offsets) & 7)) return RB200_E_ARG;
+        launch_block_decode(ctx->stream, blob, blob_size, offsets, block_freqs, n_blocks, block_size, chunk_syms, out, ctx->d_status);
+        return check_launch(ctx, "block_decode_kernel");
+    }
+    if (mem_kind != RB200_MEM_HOST) return RB200_E_ARG;
+    const size_t fbytes = static_cast<size_t>(n_blocks) * 256 * sizeof(uint16_t);
+    int rc = reserve(ctx, ctx->st_blob, blob_size + 16);
+    if (rc == RB200_OK) rc = reserve(ctx, ctx->st_offsets, (n_chunks + 1) * sizeof(uint64_t));
+    if (rc == RB200_OK) rc = reserve(ctx, ctx->st_out, n + 16);
+    if (rc == RB200_OK) rc = reserve(ctx, ctx->st_aux, fbytes);
+    if (rc != RB200_OK) return rc;
+    RB_CUDA(ctx, cudaMemcpyAsync(ctx->st_blob.p, blob, blob_size, cudaMemcpyHostToDevice, ctx->stream));
+    RB_CUDA(ctx, cudaMemcpyAsync(ctx->st_offsets.p, offsets, (n_chunks + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    RB_CUDA(ctx, cudaMemcpyAsync(ctx->st_aux.p, block_freqs, fbytes, cudaMemcpyHostToDevice, ctx->stream));
+    launch_block_decode(ctx->stream, static_cast<const uint8_t*>(ctx->st_blob.p), blob_size,
+                        static_cast<const uint64_t*>(ctx->st_offsets.p), static_cast<const uint16_t*>(ctx->st_aux.p), n_blocks,
+                        block_size, chunk_syms, static_cast<uint8_t*>(ctx->st_out.p), ctx->d_status);
+    rc = check_launch(ctx, "block_decode_kernel");
+    if (rc != RB200_OK) return rc;
+    RB_CUDA(ctx, cudaMemcpyAsync(out, ctx->st_out.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+    return rb200_sync(ctx);
+}

@@ -1,0 +1,182 @@
+"""GPU parity: the C-ABI (include/rans_b200.h) against the oracle, bit-exact.
+
+Mirrors the reference's own verification (decode-output memcmp, main_simd.cpp:340-343)
+and strengthens it: the GPU blob must equal the oracle's container byte for byte, the
+GPU must decode the oracle's blob, and the oracle must decode the GPU's blob.
+"""
+import numpy as np
+import pytest
+
+import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+WORD, ALIAS = 0, 2
+
+
+def _model(oracle_lib, data, scale_bits):
+    return oracle_lib.model(data, scale_bits)
+
+
+def _roundtrip(gpu_ctx, oracle_lib, data, coder, scale_bits, chunk):
+    import ryg_rans_b200 as rb
+    freqs, cum = _model(oracle_lib, data, scale_bits)
+    model = gpu_ctx.model(coder, scale_bits, freqs)
+    blob, offs = gpu_ctx.encode_host(model, data, chunk)
+    oblob, ooffs = oracle_lib.chunked_encode(coder, data, freqs, cum, chunk, nlanes=32, scale_bits=scale_bits)
+    assert np.array_equal(offs, ooffs), "directory differs from the oracle container"
+    assert blob.size == oblob.size
+    assert np.array_equal(blob, oblob), "GPU stream is not byte-identical to the reference-order stream"
+    # GPU decodes the oracle's blob; oracle decodes the GPU's blob
+    dec = gpu_ctx.decode_host(model, oblob, ooffs, data.size, chunk)
+    assert np.array_equal(dec, data)
+    dec2 = oracle_lib.chunked_decode(coder, blob, offs, data.size, freqs, cum, chunk, nlanes=32, scale_bits=scale_bits)
+    assert np.array_equal(dec2, data)
+    model.close()
+
+
+@pytest.mark.parametrize("kind", ["uniform", "zipf", "text", "two", "skew", "const"])
+@pytest.mark.parametrize("n,chunk", [(1, 32), (31, 32), (32, 32), (33, 64), (4096, 4096), (100003, 4096), (300000, 16384)])
+def test_word_parity(gpu_ctx, oracle_lib, gen, kind, n, chunk):
+    data = gen(kind, n, seed=n * 7 + len(kind))
+    _roundtrip(gpu_ctx, oracle_lib, data, WORD, 12, chunk)
+
+
+def test_word_empty(gpu_ctx, oracle_lib, gen):
+    freqs, cum = _model(oracle_lib, gen("uniform", 1000, 1), 12)
+    model = gpu_ctx.model(WORD, 12, freqs)
+    blob, offs = gpu_ctx.encode_host(model, np.zeros(0, np.uint8), 4096)
+    assert blob.size == 0 and offs.tolist() == [0]
+    out = gpu_ctx.decode_host(model, blob, offs, 0, 4096)
+    assert out.size == 0
+
+
+def test_word_reference_stream_n32(gpu_ctx, oracle_lib, ref_lib, gen):
+    """A single chunk IS the reference's N-way stream with N = 32 (SURVEY 8a layout)."""
+    data = gen("text", 50000, 5)
+    freqs, cum = ref_lib.model(data, 12)
+    ref_stream = ref_lib.encode(orc.CODER_WORD, data, freqs, cum, 32)
+    model = gpu_ctx.model(WORD, 12, freqs)
+    blob, offs = gpu_ctx.encode_host(model, data, 1 << 16)
+    assert np.array_equal(blob[int(offs[0]):], ref_stream)
+    # and the reference's own primitives decode the GPU stream
+    dec, used = ref_lib.decode(orc.CODER_WORD, blob[int(offs[0]):], data.size, freqs, cum, 32)
+    assert np.array_equal(dec, data) and used == ref_stream.size
+
+
+def test_word_corrupt_stream_is_reported(gpu_ctx, oracle_lib, gen):
+    import ryg_rans_b200 as rb
+    data = gen("zipf", 20000, 3)
+    freqs, cum = _model(oracle_lib, data, 12)
+    model = gpu_ctx.model(WORD, 12, freqs)
+    blob, offs = gpu_ctx.encode_host(model, data, 4096)
+    bad = blob.copy()
+    bad[int(offs[1]) + 128:int(offs[1]) + 400] ^= 0x5A
+    with pytest.raises(rb.RansError) as ei:
+        gpu_ctx.decode_host(model, bad, offs, data.size, 4096)
+    assert ei.value.code == -4
+    # truncated directory
+    offs2 = offs.copy()
+    offs2[2] = offs2[3] + 64
+    with pytest.raises(rb.RansError):
+        gpu_ctx.decode_host(model, blob, offs2, data.size, 4096)
+    # context still healthy afterwards
+    assert np.array_equal(gpu_ctx.decode_host(model, blob, offs, data.size, 4096), data)
+
+
+def test_word_zero_freq_symbol_is_reported(gpu_ctx, oracle_lib, gen):
+    import ryg_rans_b200 as rb
+    data = gen("text", 10000, 2)
+    freqs, cum = _model(oracle_lib, data, 12)
+    model = gpu_ctx.model(WORD, 12, freqs)
+    other = data.copy()
+    missing = int(np.flatnonzero(freqs == 0)[0])
+    other[1234] = missing
+    with pytest.raises(rb.RansError) as ei:
+        gpu_ctx.encode_host(model, other, 4096)
+    assert ei.value.code == -7
+
+
+def test_encode_bound_is_tight_enough(gpu_ctx, oracle_lib, gen):
+    data = gen("uniform", 70000, 9)
+    freqs, cum = _model(oracle_lib, data, 12)
+    model = gpu_ctx.model(WORD, 12, freqs)
+    blob, offs = gpu_ctx.encode_host(model, data, 4096)
+    assert blob.size <= gpu_ctx.encode_bound(data.size, 4096)
+    import ryg_rans_b200 as rb
+    with pytest.raises(rb.RansError) as ei:
+        gpu_ctx.encode_host(model, data, 4096, blob_cap=blob.size - 16)
+    assert ei.value.code == -3
+
+
+# ---------------------------------------------------------------- alias coder (BASELINE config 3)
+
+@pytest.mark.parametrize("kind", ["zipf", "uniform", "text", "two", "const"])
+@pytest.mark.parametrize("n,chunk,sb", [(1, 32, 16), (33, 64, 16), (4096, 4096, 16), (100003, 4096, 16), (300000, 16384, 16),
+                                        (50001, 2048, 12), (50001, 2048, 8)])
+def test_alias_parity(gpu_ctx, oracle_lib, gen, kind, n, chunk, sb):
+    data = gen(kind, n, seed=n * 11 + len(kind))
+    _roundtrip(gpu_ctx, oracle_lib, data, ALIAS, sb, chunk)
+
+
+def test_alias_reference_stream_n32(gpu_ctx, ref_lib, gen):
+    data = gen("zipf", 60000, 6)
+    freqs, cum = ref_lib.model(data, 16)
+    ref_stream = ref_lib.encode(orc.CODER_ALIAS, data, freqs, cum, 32, 16)
+    model = gpu_ctx.model(ALIAS, 16, freqs)
+    blob, offs = gpu_ctx.encode_host(model, data, 1 << 16)
+    assert np.array_equal(blob[int(offs[0]):], ref_stream)
+    dec, used = ref_lib.decode(orc.CODER_ALIAS, blob[int(offs[0]):], data.size, freqs, cum, 32, 16)
+    assert np.array_equal(dec, data) and used == ref_stream.size
+
+
+def test_alias_corrupt_stream_is_reported(gpu_ctx, oracle_lib, gen):
+    import ryg_rans_b200 as rb
+    data = gen("zipf", 20000, 3)
+    freqs, cum = _model(oracle_lib, data, 16)
+    model = gpu_ctx.model(ALIAS, 16, freqs)
+    blob, offs = gpu_ctx.encode_host(model, data, 4096)
+    bad = blob.copy()
+    bad[int(offs[2]) + 128:int(offs[2]) + 300] ^= 0xA5
+    with pytest.raises(rb.RansError) as ei:
+        gpu_ctx.decode_host(model, bad, offs, data.size, 4096)
+    assert ei.value.code == -4
+
+
+# ---------------------------------------------------------------- device histogram / per-block models (config 5)
+
+@pytest.mark.parametrize("n", [0, 1, 15, 16, 17, 4097, 1 << 20, (1 << 22) + 5])
+def test_histogram(gpu_ctx, gen, n):
+    data = gen("zipf", n, 4) if n else np.zeros(0, np.uint8)
+    counts = gpu_ctx.histogram(data)
+    assert np.array_equal(counts, np.bincount(data, minlength=256).astype(np.uint64))
+
+
+def _block_data(gen, n_blocks, block_size):
+    kinds = ["zipf", "uniform", "text", "two", "skew", "const"]
+    return np.concatenate([gen(kinds[b % len(kinds)], block_size, seed=1000 + b) for b in range(n_blocks)])
+
+
+@pytest.mark.parametrize("n_blocks,block_size,chunk", [(13, 65536, 8192), (7, 4096, 4096), (6, 16384, 2048), (12, 65536, 65536)])
+def test_block_models_and_roundtrip(gpu_ctx, oracle_lib, gen, n_blocks, block_size, chunk):
+    data = _block_data(gen, n_blocks, block_size)
+    freqs16 = gpu_ctx.blocks_build_models(data, n_blocks, block_size)
+    want = np.stack([oracle_lib.model(data[b * block_size:(b + 1) * block_size], 12)[0] for b in range(n_blocks)])
+    assert np.array_equal(freqs16.astype(np.uint32), want), "device normalize_freqs differs from the reference algorithm"
+
+    blob, offs = gpu_ctx.blocks_encode_host(data, n_blocks, block_size, freqs16, chunk)
+    # oracle: every block is its own container; containers concatenate because each ends 16-aligned
+    parts, all_offs, base = [], [], 0
+    for b in range(n_blocks):
+        f = want[b]
+        c = np.concatenate([[0], np.cumsum(f)]).astype(np.uint32)
+        ob, oo = oracle_lib.chunked_encode(orc.CODER_WORD, data[b * block_size:(b + 1) * block_size], f, c, chunk)
+        parts.append(ob)
+        all_offs.append(oo[:-1] + base)
+        base += ob.size
+    oblob = np.concatenate(parts)
+    ooffs = np.concatenate(all_offs + [[base]]).astype(np.uint64)
+    assert np.array_equal(offs, ooffs)
+    assert np.array_equal(blob, oblob)
+    out = gpu_ctx.blocks_decode_host(oblob, ooffs, freqs16, n_blocks, block_size, chunk)
+    assert np.array_equal(out, data)
