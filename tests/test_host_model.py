@@ -1,0 +1,121 @@
+"""CPU tests of the product's host-side code (no GPU needed): the C-ABI library loads and
+exports everything include/rans_b200.h declares, and its host model construction
+(rb200_count_freqs / normalize_freqs / word_tables_build / alias_tables_build) is
+bit-identical to the reference algorithm (via the oracle and the golden fixtures)."""
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle as orc
+import ryg_rans_b200 as rb
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLD = np.load(os.path.join(HERE, "golden", "golden.npz"))
+INDEX = json.load(open(os.path.join(HERE, "golden", "golden.json")))
+CASES = [k for k in INDEX if k != "book1"]
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "rans_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(rb200_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    lib = rb.load()
+    bound = {name for name, _, _ in rb.api.EXPORTS}
+    assert declared == bound, f"header/binding mismatch: {declared ^ bound}"
+    for name in declared:
+        assert hasattr(lib.dll, name), name
+    assert lib.dll.rb200_version() == 1
+    assert lib.dll.rb200_strerror(-4) == b"corrupt or truncated stream"
+
+
+def test_geometry_calls():
+    lib = rb.load()
+    assert lib.dll.rb200_chunk_count(0, 4096) == 0
+    assert lib.dll.rb200_chunk_count(1, 4096) == 1
+    assert lib.dll.rb200_chunk_count(8193, 4096) == 3
+    # bound = per chunk round16(128 + 2 * m)
+    assert lib.dll.rb200_encode_bound(4096, 4096) == 128 + 8192
+    assert lib.dll.rb200_encode_bound(4097, 4096) == 128 + 8192 + 144
+    assert lib.dll.rb200_encode_bound(0, 4096) == 0
+
+
+def test_no_gpu_is_a_loud_error():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible")
+    with pytest.raises(rb.RansError) as ei:
+        rb.Context(0)
+    assert ei.value.code == -5          # RB200_E_CUDA: no silent CPU fallback exists
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("sb,cname", [(12, "word"), (14, "byte"), (16, "alias")])
+def test_normalize_matches_reference_golden(case, sb, cname):
+    data = GOLD[f"{case}/data"]
+    st = rb.SymbolStats().count_freqs(data)
+    assert np.array_equal(st.freqs, np.bincount(data, minlength=256))
+    st.normalize_freqs(1 << sb)
+    assert np.array_equal(st.freqs, GOLD[f"{case}/{cname}/freqs"])
+    assert st.cum_freqs[256] == 1 << sb and np.array_equal(np.diff(st.cum_freqs.astype(np.int64)), st.freqs)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_normalize_matches_oracle_random(oracle_lib, seed):
+    rng = np.random.default_rng(seed)
+    nsym = int(rng.integers(1, 257))
+    raw = np.zeros(256, np.uint32)
+    syms = rng.permutation(256)[:nsym]
+    raw[syms] = (rng.pareto(0.7, nsym) * 50 + 1).astype(np.uint32)     # heavy tails: many squashed symbols
+    for sb in (8, 12, 16):
+        if nsym > (1 << sb):
+            continue
+        want_f, want_c = oracle_lib.normalize_freqs(raw, 1 << sb)
+        st = rb.SymbolStats()
+        st.freqs[:] = raw
+        st.normalize_freqs(1 << sb)
+        assert np.array_equal(st.freqs, want_f) and np.array_equal(st.cum_freqs, want_c)
+
+
+def test_normalize_rejects_bad_input():
+    st = rb.SymbolStats()
+    with pytest.raises(rb.RansError):
+        st.normalize_freqs(4096)             # all-zero histogram: the reference would divide by zero
+    st.freqs[:] = 1
+    with pytest.raises(rb.RansError):
+        st.normalize_freqs(128)              # main.cpp:77 assert(target_total >= 256)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_word_tables_match_reference_layout(oracle_lib, case):
+    data = GOLD[f"{case}/data"]
+    st = rb.SymbolStats().count_freqs(data).normalize_freqs(4096)
+    slots, s2s = st.word_tables()
+    oslots, os2s = oracle_lib.word_tables(st.freqs, st.cum_freqs)
+    assert np.array_equal(slots, oslots) and np.array_equal(s2s, os2s)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_alias_tables_match_reference_golden(case):
+    import hashlib
+    data = GOLD[f"{case}/data"]
+    st = rb.SymbolStats().count_freqs(data).normalize_freqs(1 << 16).make_alias_table()
+    assert np.array_equal(st.divider, GOLD[f"{case}/alias_tables/divider"])
+    assert np.array_equal(st.slot_adjust, GOLD[f"{case}/alias_tables/slot_adjust"])
+    assert np.array_equal(st.slot_freqs, GOLD[f"{case}/alias_tables/slot_freqs"])
+    assert np.array_equal(st.sym_id, GOLD[f"{case}/alias_tables/sym_id"])
+    assert hashlib.sha256(st.alias_remap.tobytes()).hexdigest() == INDEX[case]["alias_remap_sha256"]
+
+
+@pytest.mark.parametrize("sb", [8, 10, 13, 16])
+def test_alias_tables_match_oracle_other_scales(oracle_lib, gen, sb):
+    data = gen("zipf", 40000, sb)
+    st = rb.SymbolStats().count_freqs(data).normalize_freqs(1 << sb).make_alias_table()
+    want = oracle_lib.alias_build(st.freqs, st.cum_freqs)
+    got = (st.divider, st.slot_adjust, st.slot_freqs, st.sym_id, st.alias_remap)
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
