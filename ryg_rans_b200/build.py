@@ -48,6 +48,6 @@ def build(force=False, verbose=False):
         subprocess.check_call(cmd)
     exam_src = os.path.join(CSRC, "exam_gpu.cpp")
     if os.path.exists(exam_src) and (force or _stale(EXAM_PATH)):
-        subprocess.check_call([nvcc, "-O2", "-std=c++17", "-I" + os.path.join(_ROOT, "include"), "-o", EXAM_PATH, exam_src,
-                               "-L" + _HERE, "-lrans_b200", "-Xlinker", "-rpath=$ORIGIN"])
+        subprocess.check_call([shutil.which("g++") or "g++", "-O2", "-std=c++17", "-I" + os.path.join(_ROOT, "include"),
+                               "-o", EXAM_PATH, exam_src, "-L" + _HERE, "-lrans_b200", "-Wl,-rpath,$ORIGIN"])
     return LIB_PATH
