@@ -109,7 +109,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
 
@@ -301,22 +301,21 @@ def run_ours(args, rank, local_rank, world):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     total_ms, enc_ms_max, dec_ms_max = tt.tolist()
 
-    # ---- NCCL gather of the compressed blobs, timed separately
+    # ---- NCCL gather of the compressed blobs + directories, timed separately
     gather_ms = None
     if dist:
-        sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        from ryg_rans_b200.shard import gather_blobs
         g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
         dist.barrier(); torch.cuda.synchronize()
         g0.record()
-        dist.all_gather(sizes, torch.tensor([blob_size], dtype=torch.int64, device=dev))
-        mx = int(max(int(s.item()) for s in sizes))
-        bufs = [torch.empty(mx, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
-        dist.gather(blob[:mx], bufs, dst=0)
+        gblob, gdir = gather_blobs(blob[:blob_size], offsets, dst=0)
         g1.record(); torch.cuda.synchronize()
         gt = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
         dist.all_reduce(gt, op=dist.ReduceOp.MAX)
         gather_ms = gt.item()
-        del bufs
+        if rank == 0:
+            assert gblob.numel() % 16 == 0 and int(gdir[-1]) == gblob.numel()
+        del gblob, gdir
 
     # ---- e2e: host pointers through the C-ABI, copies inside the timed region
     e2e = None
@@ -354,6 +353,9 @@ def run_ours(args, rank, local_rank, world):
                "steps": args.e2e_steps, "note": "rb200_encode + rb200_decode with RB200_MEM_HOST on pinned buffers, wall clock"}
 
     if rank != 0:
+        if dist:
+            dist.barrier()
+            dist.destroy_process_group()
         return
     peak, peak_src = measured_peak()
     algo_bytes = n + blob_size                       # (1 + c) bytes per symbol
@@ -384,8 +386,9 @@ def run_ours(args, rank, local_rank, world):
             line["cpu_baseline"] = cpu_reference_run(kind, coder_name, sb, min(args.cpu_sample, n), runs=2, threads=os.cpu_count() or 1)
         except Exception as e:  # the baseline must not take the GPU number down with it
             line["cpu_baseline"] = {"error": repr(e)}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if dist:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -21,13 +21,6 @@ constexpr uint32_t kByteL = 1u << 23;   // RANS_BYTE_L, rans_byte.h:50
 constexpr int kAliasDecWarps = 8;
 constexpr int kAliasEncWarps = 8;
 
-__device__ __forceinline__ uint4 lds_u128_ro(uint32_t addr)
-{
-    uint4 v;
-    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-    return v;
-}
-
 // RansDecGetAlias (main_alias.cpp:252-267) + RansDecRenorm (rans_byte.h:307-318), warp-wide
 __device__ __forceinline__ void alias_dec_step(uint32_t& x, uint32_t& cursor, uint32_t div_tab, uint32_t dec_tab,
                                                uint32_t ring, uint8_t* o, uint32_t lt, uint32_t sb, bool active)

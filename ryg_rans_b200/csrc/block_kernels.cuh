@@ -252,30 +252,34 @@ block_encode_kernel(const uint8_t* __restrict__ in, uint32_t block_size, const u
                     uint32_t chunk_syms, uint8_t* __restrict__ scratch, uint32_t slot_bytes, uint32_t* __restrict__ sizes,
                     uint32_t* __restrict__ status)
 {
-    __shared__ __align__(16) uint2 s_tab[256 * kEncReplicas];
+    extern __shared__ __align__(1024) uint8_t s_enc[];          // [32 KiB table][warps x 1 KiB stage + ring]
     __shared__ uint32_t s_cum[257];
     __shared__ uint32_t s_flag[1];
+    uint4* s_tab = reinterpret_cast<uint4*>(s_enc);
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
     const uint16_t* freqs = block_freqs + static_cast<uint64_t>(blockIdx.x) * 256;
     const uint32_t per_block = block_size / chunk_syms;
     const bool ok = block_prefix(freqs, s_cum, &s_flag[0]);
     for (uint32_t s = tid; s < 256; s += blockDim.x) {
         const uint32_t f = ok ? s_cum[s + 1] - s_cum[s] : 0;
-        uint2 e = make_uint2(0u, kEncBadSymbol);
+        WordEncEntry e = {0u, kEncBadSymbol};
         if (f) {
             uint32_t sh = 0;
             while ((1u << sh) < f) sh++;
-            const uint64_t M = ((1ull << (32 + sh)) + f - 1) / f;          // in [2^32, 2^33)
-            e = make_uint2(static_cast<uint32_t>(M), f | (s_cum[s] << 13) | (sh << 25));
+            const uint64_t M = ((1ull << (32 + sh)) + f - 1) / f;          // in [2^32, 2^33): keep the low word
+            e.magic = static_cast<uint32_t>(M);
+            e.packed = f | (s_cum[s] << 13) | (sh << 25);
         }
+        const uint4 x = word_enc_expand(e);
 #pragma unroll
-        for (uint32_t r = 0; r < kEncReplicas; r++) s_tab[s * kEncReplicas + r] = e;
+        for (uint32_t r = 0; r < kEncReplicas; r++) s_tab[s * kEncReplicas + r] = x;
     }
     __syncthreads();
     if (warp >= per_block) return;
     const uint32_t chunk = blockIdx.x * per_block + warp;
     const uint8_t* src = in + static_cast<uint64_t>(blockIdx.x) * block_size + static_cast<uint64_t>(warp) * chunk_syms;
-    word_encode_chunk(src, chunk_syms, chunk, smem_addr(s_tab), scratch, slot_bytes, sizes, status);
+    word_encode_chunk(src, chunk_syms, chunk, smem_addr(s_enc), smem_addr(s_enc) + kEncTableBytes + warp * kEncWarpSmem, scratch,
+                      slot_bytes, sizes, status);
 }
 
 inline uint32_t block_threads(uint32_t block_size, uint32_t chunk_syms)
@@ -289,14 +293,16 @@ inline void configure_block_kernels()
 {
     cudaFuncSetAttribute(block_decode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(block_encode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(block_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncTableBytes + kMaxBlockWarps * kEncWarpSmem);
 }
 
 inline void launch_block_encode(cudaStream_t stream, const uint8_t* d_in, uint32_t n_blocks, uint32_t block_size,
                                 const uint16_t* d_freqs, uint32_t chunk_syms, uint8_t* scratch, uint32_t slot,
                                 uint32_t* sizes, uint32_t* status)
 {
-    block_encode_kernel<<<n_blocks, block_threads(block_size, chunk_syms), 0, stream>>>(d_in, block_size, d_freqs, chunk_syms,
-                                                                                         scratch, slot, sizes, status);
+    const uint32_t threads = block_threads(block_size, chunk_syms);
+    block_encode_kernel<<<n_blocks, threads, kEncTableBytes + (threads / 32) * kEncWarpSmem, stream>>>(d_in, block_size, d_freqs, chunk_syms,
+                                                                                                       scratch, slot, sizes, status);
 }
 
 inline void launch_block_decode(cudaStream_t stream, const uint8_t* blob, uint64_t blob_size, const uint64_t* offsets,

@@ -61,6 +61,13 @@ __device__ __forceinline__ uint2 lds_u64_ro(uint32_t addr)
     asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ uint4 lds_u128_ro(uint32_t addr)
+{
+    uint4 v;
+    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+
 __device__ __forceinline__ uint2 lds_u64(uint32_t addr)
 {
     uint2 v;

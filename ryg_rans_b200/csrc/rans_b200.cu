@@ -178,6 +178,7 @@ extern "C" int rb200_ctx_create(rb200_ctx** out, int device, void* stream)
     cudaFuncSetAttribute(word_decode_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(word_decode_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(word_encode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(word_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmemBytes);
     configure_alias_kernels();
     configure_block_kernels();
     cudaGetLastError();
@@ -314,6 +315,45 @@ extern "C" size_t rb200_encode_bound(size_t n, uint32_t chunk_syms)
 
 namespace {
 
+
+// directory + compaction after any encode kernel: sizes[] -> offsets[] + blob
+int finish_encode(rb200_ctx* ctx, uint8_t* scratch, uint32_t slot, uint32_t* sizes, uint64_t* tile_sums, uint32_t n_chunks,
+                  uint8_t* d_blob, size_t blob_cap, uint64_t* d_offsets)
+{
+    if (!n_chunks) {
+        RB_CUDA(ctx, cudaMemsetAsync(d_offsets, 0, sizeof(uint64_t), ctx->stream));
+        return RB200_OK;
+    }
+    const uint32_t tiles = (n_chunks + kScanTile - 1) / kScanTile;
+    scan_tiles_kernel<<<tiles, 1024, 0, ctx->stream>>>(sizes, n_chunks, d_offsets, tile_sums);
+    int rc = check_launch(ctx, "scan_tiles_kernel");
+    if (rc != RB200_OK) return rc;
+    const uint32_t prefixed = tiles > kTilePrefixThreshold ? 1u : 0u;
+    if (prefixed) {
+        tile_prefix_kernel<<<1, 1024, 0, ctx->stream>>>(tile_sums, tiles);
+        rc = check_launch(ctx, "tile_prefix_kernel");
+        if (rc != RB200_OK) return rc;
+    }
+    const uint32_t grid = (n_chunks + kCopyWarps - 1) / kCopyWarps;
+    compact_kernel<<<grid, kCopyWarps * 32, 0, ctx->stream>>>(scratch, slot, sizes, d_offsets, tile_sums, prefixed, n_chunks, d_blob,
+                                                               blob_cap, ctx->d_status);
+    return check_launch(ctx, "compact_kernel");
+}
+
+int reserve_encode_workspace(rb200_ctx* ctx, uint32_t n_chunks, uint32_t slot, uint8_t** scratch, uint32_t** sizes, uint64_t** tile_sums)
+{
+    int rc = reserve(ctx, ctx->scratch, static_cast<size_t>(n_chunks) * slot + 16);
+    if (rc != RB200_OK) return rc;
+    const size_t sizes_bytes = round16((static_cast<size_t>(n_chunks) + 1) * sizeof(uint32_t));
+    const size_t tiles = (static_cast<size_t>(n_chunks) + kScanTile - 1) / kScanTile + 1;
+    rc = reserve(ctx, ctx->sizes, sizes_bytes + tiles * sizeof(uint64_t));
+    if (rc != RB200_OK) return rc;
+    *scratch = static_cast<uint8_t*>(ctx->scratch.p);
+    *sizes = static_cast<uint32_t*>(ctx->sizes.p);
+    *tile_sums = reinterpret_cast<uint64_t*>(static_cast<uint8_t*>(ctx->sizes.p) + sizes_bytes);
+    return RB200_OK;
+}
+
 int encode_device(rb200_ctx* ctx, const rb200_model* model, const uint8_t* d_in, size_t n, uint32_t chunk_syms,
                   uint8_t* d_blob, size_t blob_cap, uint64_t* d_offsets)
 {
@@ -321,17 +361,14 @@ int encode_device(rb200_ctx* ctx, const rb200_model* model, const uint8_t* d_in,
     if (n_chunks_sz >= (1ull << 31)) return RB200_E_ARG;
     const uint32_t n_chunks = static_cast<uint32_t>(n_chunks_sz);
     const uint32_t slot = slot_bytes_for(chunk_syms);
-    int rc = reserve(ctx, ctx->scratch, static_cast<size_t>(n_chunks) * slot + 16);
+    uint8_t* scratch; uint32_t* sizes; uint64_t* tile_sums;
+    int rc = reserve_encode_workspace(ctx, n_chunks, slot, &scratch, &sizes, &tile_sums);
     if (rc != RB200_OK) return rc;
-    rc = reserve(ctx, ctx->sizes, (static_cast<size_t>(n_chunks) + 1) * sizeof(uint32_t));
-    if (rc != RB200_OK) return rc;
-    uint8_t* scratch = static_cast<uint8_t*>(ctx->scratch.p);
-    uint32_t* sizes = static_cast<uint32_t*>(ctx->sizes.p);
     if (n_chunks) {
         if (model->coder == RB200_CODER_WORD) {
             const uint32_t grid = (n_chunks + kEncWarps - 1) / kEncWarps;
-            word_encode_kernel<<<grid, kEncWarps * 32, 0, ctx->stream>>>(d_in, n, chunk_syms, n_chunks, model->d_word_enc,
-                                                                          scratch, slot, sizes, ctx->d_status);
+            word_encode_kernel<<<grid, kEncWarps * 32, kEncSmemBytes, ctx->stream>>>(d_in, n, chunk_syms, n_chunks, model->d_word_enc,
+                                                                                      scratch, slot, sizes, ctx->d_status);
             rc = check_launch(ctx, "word_encode_kernel");
         } else {
             rc = launch_alias_encode(ctx->stream, d_in, n, chunk_syms, n_chunks, model->scale_bits, model->d_alias_enc,
@@ -340,15 +377,7 @@ int encode_device(rb200_ctx* ctx, const rb200_model* model, const uint8_t* d_in,
         }
         if (rc != RB200_OK) return rc;
     }
-    directory_scan_kernel<<<1, 1024, 0, ctx->stream>>>(sizes, n_chunks, d_offsets, blob_cap, ctx->d_status);
-    rc = check_launch(ctx, "directory_scan_kernel");
-    if (rc != RB200_OK) return rc;
-    if (n_chunks) {
-        const uint32_t grid = (n_chunks + kCopyWarps - 1) / kCopyWarps;
-        compact_kernel<<<grid, kCopyWarps * 32, 0, ctx->stream>>>(scratch, slot, sizes, d_offsets, n_chunks, d_blob, blob_cap);
-        rc = check_launch(ctx, "compact_kernel");
-    }
-    return rc;
+    return finish_encode(ctx, scratch, slot, sizes, tile_sums, n_chunks, d_blob, blob_cap, d_offsets);
 }
 
 int decode_device(rb200_ctx* ctx, const rb200_model* model, const uint8_t* d_blob, size_t blob_size, const uint64_t* d_offsets,
@@ -391,7 +420,7 @@ extern "C" int rb200_encode(rb200_ctx* ctx, const rb200_model* model, const uint
     if (mem_kind != RB200_MEM_HOST) return RB200_E_ARG;
     // host buffers: stage in, run, stage out; synchronous like the reference's loops
     const size_t bound = rb200_encode_bound(n, chunk_syms);
-    const size_t dev_cap = bound < blob_cap ? bound : round16(blob_cap) > blob_cap ? blob_cap & ~static_cast<size_t>(15) : blob_cap;
+    const size_t dev_cap = bound;   // the staging blob is always worst-case sized; blob_cap is checked after the directory is known
     int rc = reserve(ctx, ctx->st_in, n + 16);
     if (rc == RB200_OK) rc = reserve(ctx, ctx->st_blob, bound + 16);
     if (rc == RB200_OK) rc = reserve(ctx, ctx->st_offsets, (n_chunks + 1) * sizeof(uint64_t));
@@ -512,20 +541,13 @@ int blocks_encode_device(rb200_ctx* ctx, const uint8_t* d_in, uint32_t n_blocks,
     if (n_chunks64 >= (1ull << 31)) return RB200_E_ARG;
     const uint32_t n_chunks = static_cast<uint32_t>(n_chunks64);
     const uint32_t slot = slot_bytes_for(chunk_syms);
-    int rc = reserve(ctx, ctx->scratch, static_cast<size_t>(n_chunks) * slot + 16);
-    if (rc == RB200_OK) rc = reserve(ctx, ctx->sizes, (static_cast<size_t>(n_chunks) + 1) * sizeof(uint32_t));
+    uint8_t* scratch; uint32_t* sizes; uint64_t* tile_sums;
+    int rc = reserve_encode_workspace(ctx, n_chunks, slot, &scratch, &sizes, &tile_sums);
     if (rc != RB200_OK) return rc;
-    uint8_t* scratch = static_cast<uint8_t*>(ctx->scratch.p);
-    uint32_t* sizes = static_cast<uint32_t*>(ctx->sizes.p);
     launch_block_encode(ctx->stream, d_in, n_blocks, block_size, d_freqs, chunk_syms, scratch, slot, sizes, ctx->d_status);
     rc = check_launch(ctx, "block_encode_kernel");
     if (rc != RB200_OK) return rc;
-    directory_scan_kernel<<<1, 1024, 0, ctx->stream>>>(sizes, n_chunks, d_offsets, blob_cap, ctx->d_status);
-    rc = check_launch(ctx, "directory_scan_kernel");
-    if (rc != RB200_OK) return rc;
-    const uint32_t grid = (n_chunks + kCopyWarps - 1) / kCopyWarps;
-    compact_kernel<<<grid, kCopyWarps * 32, 0, ctx->stream>>>(scratch, slot, sizes, d_offsets, n_chunks, d_blob, blob_cap);
-    return check_launch(ctx, "compact_kernel");
+    return finish_encode(ctx, scratch, slot, sizes, tile_sums, n_chunks, d_blob, blob_cap, d_offsets);
 }
 
 bool blocks_geometry_ok(uint32_t n_blocks, uint32_t block_size, uint32_t chunk_syms)

@@ -177,117 +177,201 @@ word_decode_kernel(const uint8_t* __restrict__ blob, uint64_t blob_size, const u
 
 // ---------------------------------------------------------------------------
 // K2: 32-way word-coder encode into per-chunk worst-case slots of a scratch buffer
+//
+// Per warp: 512 B input stage (16 steps of symbols, filled by one coalesced 128-bit load
+// per lane issued a block ahead) and a 512 B output ring (emitted words are placed with
+// ballot/popc compaction, flushed to HBM as whole 16-byte vectors).  The per-symbol
+// parameters come from ONE conflict-free LDS.128: the 256-entry table is replicated 8x so
+// that the 8 lanes of a quarter-warp always hit different 16-byte bank groups.
 // ---------------------------------------------------------------------------
-constexpr int kEncWarps = 8;
-constexpr uint32_t kEncReplicas = 16;   // copies of the 256-entry table: lane l reads copy l & 15 -> conflict-free LDS.64
+constexpr int kEncWarps = 16;
+constexpr uint32_t kEncReplicas = 8;
+constexpr uint32_t kEncStageBytes = 512;     // 16 steps x 32 symbols
+constexpr uint32_t kEncRingBytes = 512;
+constexpr uint32_t kEncTableBytes = 256 * kEncReplicas * 16;                 // 32 KiB
+constexpr uint32_t kEncWarpSmem = kEncStageBytes + kEncRingBytes;            // 1 KiB per warp
 
-__device__ __forceinline__ void word_enc_step(uint32_t& x, uint32_t& emitted, uint32_t& flags, uint32_t sym,
-                                              uint32_t tab_lane /*shared addr of this lane's replica*/, uint16_t* slot_end,
-                                              uint32_t gt, bool active)
+// {magic, x_max | shift, start, 4096 - freq}
+//   x_max = freq << 20 in 32-bit arithmetic (rans_word_sse41.h:85; wraps to 0 for freq 4096, as the
+//   reference does); its low 20 bits are zero, so the 4-bit reciprocal shift rides in them:
+//   x >= x_max  <=>  (x | 31) >= (x_max | shift), and the funnel shift only looks at the low 5 bits.
+__device__ __forceinline__ uint4 word_enc_expand(WordEncEntry e)
+{
+    const uint32_t freq = e.packed & 0x1fffu, start = (e.packed >> 13) & 0xfffu, shift = (e.packed >> 25) & 0xfu;
+    return make_uint4(e.magic, (freq << 20) | shift, start, kWordSlots - freq);    // freq 0 (bad symbol) <=> w == 4096
+}
+
+__device__ __forceinline__ uint32_t funnel_shr_wrap(uint32_t lo, uint32_t hi, uint32_t n)
+{
+    uint32_t r;
+    asm("shf.r.wrap.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(lo), "r"(hi), "r"(n));
+    return r;
+}
+
+struct WordEncState {
+    uint32_t x;        // rANS state
+    uint32_t wpos;     // ring byte position (relative to slot end, un-wrapped) of the next word = 510 - 2 * words_emitted
+    uint32_t flags;    // OR of the table's (4096 - freq) words: bit 12 set <=> a symbol with freq 0 was met
+};
+
+// RansWordEncPut for 32 lanes (rans_word_sse41.h:81-93)
+__device__ __forceinline__ void word_enc_step(WordEncState& st, uint32_t sym, uint32_t tab_lane, uint32_t ring, uint32_t gt, bool active)
 {
     bool need = false;
-    uint32_t magic = 0, freq = 1, start = 0, shift = 0;
+    uint4 e = make_uint4(0, 0, 0, 0);
     if (active) {
-        const uint2 ent = lds_u64_ro(tab_lane + sym * (kEncReplicas * 8));
-        magic = ent.x;
-        freq = ent.y & 0x1fffu;
-        start = (ent.y >> 13) & 0xfffu;
-        shift = (ent.y >> 25) & 0xfu;
-        flags |= ent.y;
-        need = x >= (freq << 20);            // ((L >> 12) << 16) * freq in 32-bit arithmetic, rans_word_sse41.h:85
+        e = lds_u128_ro(tab_lane + sym * (kEncReplicas * 16));
+        st.flags |= e.w;
+        need = (st.x | 31u) >= e.y;                                   // x >= ((L >> 12) << 16) * freq, :85
     }
     const uint32_t mask = __ballot_sync(0xffffffffu, need);
     if (need) {
-        slot_end[-static_cast<int64_t>(emitted + 1 + __popc(mask & gt))] = static_cast<uint16_t>(x);   // :86-87
-        x >>= 16;                                                                                      // :88
+        sts_u16(ring | ((st.wpos - 2u * __popc(mask & gt)) & (kEncRingBytes - 1)), st.x);   // :86-87, lanes 31..0 downwards
+        st.x >>= 16;                                                                        // :88
     }
-    emitted += __popc(mask);
+    st.wpos -= 2u * __popc(mask);
     if (active) {
-        // q = x / freq exactly: M = 2^32 + magic = ceil(2^(32+shift) / freq)
-        const uint32_t q = static_cast<uint32_t>((static_cast<uint64_t>(x) + __umulhi(x, magic)) >> shift);
-        x = x + start + q * (kWordSlots - freq);          // == ((x/freq) << 12) + x%freq + start, :92
+        // q = x / freq exactly: M = 2^32 + magic = ceil(2^(32+shift) / freq), q = (x + mulhi(x, magic)) >> shift
+        const uint32_t hi = __umulhi(st.x, e.x);
+        const uint32_t lo = st.x + hi;
+        const uint32_t q = funnel_shr_wrap(lo, lo < hi ? 1u : 0u, e.y);
+        st.x = st.x + e.z + q * e.w;                       // ((x / freq) << 12) + x % freq + start, :92
     }
 }
 
-// Encode chunk `chunk` (one warp) into the END of its scratch slot; s_tab = shared address of
-// the 16x replicated {magic, packed} table.
+// flush every complete 16-byte vector of the ring; *flushed = bytes already written below slot_end
+__device__ __forceinline__ void word_enc_flush(uint32_t produced, uint32_t& flushed, uint32_t ring, uint8_t* slot_end, uint32_t lane)
+{
+    const uint32_t nvec = (produced - flushed) >> 4;
+    __syncwarp();
+    if (lane < nvec) {
+        const uint32_t v = (flushed >> 4) + lane + 1;                 // vector v ends 16 * (v - 1) bytes below slot_end
+        const uint4 q = lds_u128(ring + ((0u - 16u * v) & (kEncRingBytes - 1)));
+        stg_stream_u128(reinterpret_cast<uint4*>(slot_end - 16ull * v), q);
+    }
+    flushed += nvec << 4;
+    __syncwarp();
+}
+
+// Encode chunk `chunk` (one warp) into the END of its scratch slot.
+//   tab  = shared address of the 8x replicated uint4 table
+//   wsm  = shared address of this warp's 1 KiB (stage, then ring; 512-byte aligned)
 __device__ __forceinline__ void word_encode_chunk(const uint8_t* __restrict__ chunk_in, uint32_t m, uint32_t chunk,
-                                                  uint32_t s_tab, uint8_t* __restrict__ scratch, uint32_t slot_bytes,
-                                                  uint32_t* __restrict__ sizes, uint32_t* __restrict__ status)
+                                                  uint32_t tab, uint32_t wsm, uint8_t* __restrict__ scratch,
+                                                  uint32_t slot_bytes, uint32_t* __restrict__ sizes, uint32_t* __restrict__ status)
 {
     const uint32_t lane = threadIdx.x & 31;
-    const uint8_t* src = chunk_in + lane;
-    uint16_t* slot_end = reinterpret_cast<uint16_t*>(scratch + static_cast<uint64_t>(chunk + 1) * slot_bytes);
-    const uint32_t tab_lane = s_tab + (lane & (kEncReplicas - 1)) * 8;
+    const uint32_t stage = wsm, ring = wsm + kEncStageBytes;
+    uint8_t* slot_end = scratch + static_cast<uint64_t>(chunk + 1) * slot_bytes;
+    const uint32_t tab_lane = tab + (lane & (kEncReplicas - 1)) * 16;
     const uint32_t gt = lanemask_gt();
 
-    uint32_t x = kWordL;                       // RansWordEncInit, rans_word_sse41.h:75-78
-    uint32_t emitted = 0, flags = 0;
+    WordEncState st;
+    st.x = kWordL;                              // RansWordEncInit, rans_word_sse41.h:75-78
+    st.wpos = kEncRingBytes - 2;
+    st.flags = 0;
+    uint32_t flushed = 0;
     const uint32_t steps = m >> 5, rem = m & 31;
+    const uint32_t nblk = steps >> 4;           // full 16-step blocks, staged; the rest is read directly
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(chunk_in) & 15) == 0;
 
-    // symbols are walked last to first (main_simd.cpp:294): ragged tail step first
+    // symbols are walked last to first (main_simd.cpp:294): ragged tail first
+    uint4 parked = make_uint4(0, 0, 0, 0);
+    if (nblk && vec_ok) parked = ldg_stream_u128(reinterpret_cast<const uint4*>(chunk_in + (nblk - 1) * kEncStageBytes) + lane);
     if (rem) {
         const bool active = lane < rem;
-        const uint32_t s = active ? src[static_cast<uint64_t>(steps) * 32] : 0;
-        word_enc_step(x, emitted, flags, s, tab_lane, slot_end, gt, active);
+        const uint32_t s = active ? chunk_in[static_cast<uint64_t>(steps) * 32 + lane] : 0;
+        word_enc_step(st, s, tab_lane, ring, gt, active);
     }
-    uint32_t g = steps;
-    for (; g >= 4; g -= 4) {
-        const uint8_t* p = src + static_cast<uint64_t>(g - 4) * 32;
-        const uint32_t s3 = p[96], s2 = p[64], s1 = p[32], s0 = p[0];
-        word_enc_step(x, emitted, flags, s3, tab_lane, slot_end, gt, true);
-        word_enc_step(x, emitted, flags, s2, tab_lane, slot_end, gt, true);
-        word_enc_step(x, emitted, flags, s1, tab_lane, slot_end, gt, true);
-        word_enc_step(x, emitted, flags, s0, tab_lane, slot_end, gt, true);
+    for (uint32_t g = steps; g > nblk * 16; g--) {
+        const uint32_t s = chunk_in[static_cast<uint64_t>(g - 1) * 32 + lane];
+        word_enc_step(st, s, tab_lane, ring, gt, true);
+        if (((g - 1) & 3) == 0) word_enc_flush(kEncRingBytes - 2 - st.wpos, flushed, ring, slot_end, lane);
     }
-    for (; g >= 1; g--) {
-        const uint32_t s = src[static_cast<uint64_t>(g - 1) * 32];
-        word_enc_step(x, emitted, flags, s, tab_lane, slot_end, gt, true);
+    word_enc_flush(kEncRingBytes - 2 - st.wpos, flushed, ring, slot_end, lane);
+
+    for (uint32_t b = nblk; b-- > 0;) {
+        __syncwarp();
+        if (vec_ok) {
+            sts_u128(stage + lane * 16, parked);
+            if (b) parked = ldg_stream_u128(reinterpret_cast<const uint4*>(chunk_in + (b - 1) * kEncStageBytes) + lane);
+        } else {                                 // unaligned input: byte loads into the stage
+            const uint8_t* p = chunk_in + b * kEncStageBytes + lane;
+#pragma unroll
+            for (int j = 0; j < 16; j++) sts_u8(stage + j * 32 + lane, p[j * 32]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int grp = 3; grp >= 0; grp--) {
+#pragma unroll
+            for (int j = 3; j >= 0; j--)
+                word_enc_step(st, lds_u8(stage + (grp * 4 + j) * 32 + lane), tab_lane, ring, gt, true);
+            // <= 256 bytes per 4 steps; flushing whenever >= 256 are pending keeps the 512-byte ring safe
+            if (kEncRingBytes - 2 - st.wpos - flushed >= 256) word_enc_flush(kEncRingBytes - 2 - st.wpos, flushed, ring, slot_end, lane);
+        }
     }
 
-    // RansWordEncFlush for lanes 31..0 (main_simd.cpp:298-299): lane 0 ends up first in memory
-    uint16_t* head = slot_end - emitted - 64;
-    head[2 * lane] = static_cast<uint16_t>(x);
-    head[2 * lane + 1] = static_cast<uint16_t>(x >> 16);
-    if (lane == 0) sizes[chunk] = kHeaderBytes + 2u * emitted;
-    if (__any_sync(0xffffffffu, (flags & kEncBadSymbol) != 0) && lane == 0) atomicOr(status, kStatSymbol);
+    // RansWordEncFlush for lanes 31..0 (main_simd.cpp:298-299): lane 31's hi word first (highest), lane 0's lo word last
+    word_enc_flush(kEncRingBytes - 2 - st.wpos, flushed, ring, slot_end, lane);     // < 16 bytes stay pending
+    const uint32_t hpos = st.wpos - 4u * (31 - lane);
+    sts_u16(ring | (hpos & (kEncRingBytes - 1)), st.x >> 16);
+    sts_u16(ring | ((hpos - 2) & (kEncRingBytes - 1)), st.x);
+    st.wpos -= kHeaderBytes;
+    const uint32_t produced = kEncRingBytes - 2 - st.wpos;           // total stream bytes
+    word_enc_flush(produced, flushed, ring, slot_end, lane);
+    const uint32_t left = produced - flushed;                        // < 16, even: head of the stream, not vector aligned
+    if (2 * lane < left) {
+        const uint32_t off = flushed + 2 * lane + 2;                 // bytes below slot_end
+        *reinterpret_cast<uint16_t*>(slot_end - off) = static_cast<uint16_t>(lds_u16(ring | ((0u - off) & (kEncRingBytes - 1))));
+    }
+    if (lane == 0) sizes[chunk] = produced;
+    if (__any_sync(0xffffffffu, (st.flags & kWordSlots) != 0) && lane == 0) atomicOr(status, kStatSymbol);
 }
 
-__global__ void __launch_bounds__(kEncWarps * 32, 4)
+__global__ void __launch_bounds__(kEncWarps * 32, 3)
 word_encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_syms, uint32_t n_chunks,
                    const WordEncEntry* __restrict__ g_table, uint8_t* __restrict__ scratch, uint32_t slot_bytes,
                    uint32_t* __restrict__ sizes, uint32_t* __restrict__ status)
 {
-    __shared__ __align__(16) uint2 s_tab[256 * kEncReplicas];   // 32 KiB
-    for (uint32_t i = threadIdx.x; i < 256 * kEncReplicas; i += blockDim.x) {
-        const WordEncEntry e = g_table[i / kEncReplicas];
-        s_tab[i] = make_uint2(e.magic, e.packed);
-    }
+    extern __shared__ __align__(1024) uint8_t s_enc[];     // [32 KiB table][warps x 1 KiB]
+    uint4* s_tab = reinterpret_cast<uint4*>(s_enc);
+    for (uint32_t i = threadIdx.x; i < 256 * kEncReplicas; i += blockDim.x) s_tab[i] = word_enc_expand(g_table[i / kEncReplicas]);
     __syncthreads();
 
-    const uint32_t chunk = blockIdx.x * kEncWarps + (threadIdx.x >> 5);
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t chunk = blockIdx.x * kEncWarps + warp;
     if (chunk >= n_chunks) return;
     const uint64_t first = static_cast<uint64_t>(chunk) * chunk_syms;
     const uint32_t m = static_cast<uint32_t>(min(static_cast<uint64_t>(chunk_syms), n - first));
-    word_encode_chunk(in + first, m, chunk, smem_addr(s_tab), scratch, slot_bytes, sizes, status);
+    word_encode_chunk(in + first, m, chunk, smem_addr(s_enc), smem_addr(s_enc) + kEncTableBytes + warp * kEncWarpSmem, scratch,
+                      slot_bytes, sizes, status);
 }
+constexpr uint32_t kEncSmemBytes = kEncTableBytes + kEncWarps * kEncWarpSmem;
 
 // ---------------------------------------------------------------------------
-// K6: directory scan + compaction of the per-chunk slots into the final blob
-// ---------------------------------------------------------------------------
-
+// K6: directory + compaction of the per-chunk slots into the final blob
+//
 // offsets[c] = E_c - sizes[c], E_c = sum_{j<=c} round_up_16(sizes[j]); offsets[n_chunks] = E_last.
-// One CTA; n_chunks is at most a few hundred thousand.
+// Pass 1 (scan_tiles_kernel, one CTA per 4096 chunks): tile-local inclusive ends into offsets[],
+// tile totals into tile_sums[].  Pass 2 (compact_kernel): every CTA adds the totals of the tiles
+// before its own (a handful of values), finalises its directory entries and moves its streams.
+// ---------------------------------------------------------------------------
+constexpr uint32_t kScanTile = 4096;
+
 __global__ void __launch_bounds__(1024)
-directory_scan_kernel(const uint32_t* __restrict__ sizes, uint32_t n_chunks, uint64_t* __restrict__ offsets,
-                      uint64_t blob_cap, uint32_t* __restrict__ status)
+scan_tiles_kernel(const uint32_t* __restrict__ sizes, uint32_t n_chunks, uint64_t* __restrict__ offsets,
+                  uint64_t* __restrict__ tile_sums)
 {
     __shared__ uint64_t s_warp[32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t per = (n_chunks + blockDim.x - 1) / blockDim.x;
-    const uint32_t lo = min(n_chunks, tid * per), hi = min(n_chunks, lo + per);
+    const uint32_t c0 = blockIdx.x * kScanTile + tid * 4;
+    uint32_t pad[4];
     uint64_t sum = 0;
-    for (uint32_t c = lo; c < hi; c++) sum += (sizes[c] + 15u) & ~15u;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        pad[j] = (c0 + j < n_chunks) ? ((sizes[c0 + j] + 15u) & ~15u) : 0u;
+        sum += pad[j];
+    }
     uint64_t incl = sum;
     for (int d = 1; d < 32; d <<= 1) {
         const uint64_t v = __shfl_up_sync(0xffffffffu, incl, d);
@@ -305,31 +389,87 @@ directory_scan_kernel(const uint32_t* __restrict__ sizes, uint32_t n_chunks, uin
     }
     __syncthreads();
     uint64_t run = incl - sum + (warp ? s_warp[warp - 1] : 0);
-    for (uint32_t c = lo; c < hi; c++) {
-        const uint32_t sz = sizes[c];
-        run += (sz + 15u) & ~15u;
-        offsets[c] = run - sz;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        run += pad[j];
+        if (c0 + j < n_chunks) offsets[c0 + j] = run;
     }
-    if (tid == blockDim.x - 1) {
-        const uint64_t total = s_warp[31];
-        offsets[n_chunks] = total;
-        if (total > blob_cap) atomicOr(status, kStatSpace);
+    if (tid == 1023) tile_sums[blockIdx.x] = s_warp[31];
+}
+
+// for very large directories: turn tile_sums into exclusive prefixes once, so compact CTAs read one value
+__global__ void __launch_bounds__(1024)
+tile_prefix_kernel(uint64_t* __restrict__ tile_sums, uint32_t n_tiles)
+{
+    __shared__ uint64_t s_warp[32];
+    __shared__ uint64_t s_carry;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_tiles; base += 1024) {
+        const uint32_t i = base + tid;
+        const uint64_t v = i < n_tiles ? tile_sums[i] : 0;
+        uint64_t incl = v;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t u = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= static_cast<uint32_t>(d)) incl += u;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint64_t w = s_warp[lane];
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint64_t u = __shfl_up_sync(0xffffffffu, w, d);
+                if (lane >= static_cast<uint32_t>(d)) w += u;
+            }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const uint64_t excl = s_carry + (warp ? s_warp[warp - 1] : 0) + incl - v;
+        if (i < n_tiles) tile_sums[i] = excl;
+        __syncthreads();
+        if (tid == 0) s_carry += s_warp[31];
+        __syncthreads();
     }
 }
 
 constexpr int kCopyWarps = 8;
+constexpr uint32_t kTilePrefixThreshold = 256;   // above this many tiles, tile_prefix_kernel runs first
 
 // one warp moves one chunk stream from the end of its scratch slot to blob[offsets[c]..E_c)
 __global__ void __launch_bounds__(kCopyWarps * 32)
 compact_kernel(const uint8_t* __restrict__ scratch, uint32_t slot_bytes, const uint32_t* __restrict__ sizes,
-               const uint64_t* __restrict__ offsets, uint32_t n_chunks, uint8_t* __restrict__ blob, uint64_t blob_cap)
+               uint64_t* __restrict__ offsets, const uint64_t* __restrict__ tile_sums, uint32_t tiles_prefixed,
+               uint32_t n_chunks, uint8_t* __restrict__ blob, uint64_t blob_cap, uint32_t* __restrict__ status)
 {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t chunk = blockIdx.x * kCopyWarps + (threadIdx.x >> 5);
+    __shared__ uint64_t s_base;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t chunk0 = blockIdx.x * kCopyWarps;
+    if (warp == 0) {      // all chunks of this CTA live in one scan tile (kScanTile % kCopyWarps == 0)
+        const uint32_t tile = chunk0 / kScanTile;
+        uint64_t acc = 0;
+        if (tiles_prefixed) {
+            acc = tile_sums[tile];
+        } else {
+            for (uint32_t t = lane; t < tile; t += 32) acc += tile_sums[t];
+            for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+        }
+        if (lane == 0) s_base = acc;
+    }
+    __syncthreads();
+    const uint32_t chunk = chunk0 + warp;
     if (chunk >= n_chunks) return;
     const uint32_t size = sizes[chunk];
-    const uint64_t off = offsets[chunk];
-    const uint64_t end = off + size;                       // multiple of 16
+    const uint64_t end = s_base + offsets[chunk];          // E_c, multiple of 16 (tile-local value from pass 1)
+    const uint64_t off = end - size;
+    __syncwarp();
+    if (lane == 0) {
+        offsets[chunk] = off;
+        if (chunk == n_chunks - 1) {
+            offsets[n_chunks] = end;
+            if (end > blob_cap) atomicOr(status, kStatSpace);
+        }
+    }
     if (end > blob_cap) return;
     const uint32_t padded = (size + 15u) & ~15u;
     const uint32_t gap = padded - size;                    // zero bytes in front of the stream, < 16
