@@ -6,7 +6,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(_HERE, "librans_b200.so")
+LIB_PATH = os.environ.get("RB200_LIB") or os.path.join(_HERE, "librans_b200.so")   # RB200_LIB: A/B-test another build
 EXAM_PATH = os.path.join(_HERE, "exam_gpu")
 
 NVCC_FLAGS = [

@@ -41,6 +41,12 @@ struct rb200_ctx {
     DevBuf scratch, sizes;
     // staging for RB200_MEM_HOST calls
     DevBuf st_in, st_blob, st_offsets, st_out, st_aux;
+    // host-mode slice pipeline: H2D on s_in, kernels on `stream`, D2H on s_out
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    static constexpr int kMaxSlices = 256;
+    cudaEvent_t ev_in[kMaxSlices] = {}, ev_done[kMaxSlices] = {};
+    cudaEvent_t ev_start = nullptr, ev_out = nullptr;
+    uint64_t* h_slice_total = nullptr;   // pinned, kMaxSlices entries
 };
 
 struct rb200_model {
@@ -174,6 +180,19 @@ extern "C" int rb200_ctx_create(rb200_ctx** out, int device, void* stream)
         return RB200_E_CUDA;
     }
     *ctx->h_status = 0;
+    e = cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_out, cudaEventDisableTiming);
+    for (int i = 0; i < rb200_ctx::kMaxSlices && e == cudaSuccess; i++) {
+        e = cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_slice_total, rb200_ctx::kMaxSlices * sizeof(uint64_t));
+    if (e != cudaSuccess) {
+        rb200_ctx_destroy(ctx);
+        return RB200_E_CUDA;
+    }
     // the decoders want the large shared-memory carve-out (tables + per-warp rings)
     cudaFuncSetAttribute(word_decode_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(word_decode_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -195,6 +214,15 @@ extern "C" void rb200_ctx_destroy(rb200_ctx* ctx)
     release(ctx->st_in); release(ctx->st_blob); release(ctx->st_offsets); release(ctx->st_out); release(ctx->st_aux);
     if (ctx->d_status) cudaFree(ctx->d_status);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
+    if (ctx->h_slice_total) cudaFreeHost(ctx->h_slice_total);
+    for (int i = 0; i < rb200_ctx::kMaxSlices; i++) {
+        if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
+        if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
+    }
+    if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+    if (ctx->ev_out) cudaEventDestroy(ctx->ev_out);
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     delete ctx;
 }
 
@@ -407,39 +435,159 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 
 }  // namespace
 
+namespace {
+
+// symbols per pipeline slice: big enough that PCIe time dwarfs launch overhead, small enough to overlap
+size_t slice_symbols(size_t n, uint32_t chunk_syms)
+{
+    size_t target = 32u << 20;
+    if (n / target >= static_cast<size_t>(rb200_ctx::kMaxSlices)) target = n / (rb200_ctx::kMaxSlices - 1);
+    size_t chunks = (target + chunk_syms - 1) / chunk_syms;
+    if (chunks == 0) chunks = 1;
+    return chunks * static_cast<size_t>(chunk_syms);
+}
+
+// Host buffers -> blob, overlapped: slice i+1 is copied in while slice i is encoded and slice i-1 is
+// copied out.  Every slice is its own container in a staging region; because containers end 16-byte
+// aligned they concatenate, and the directory entries only need the running base added.
+int encode_host(rb200_ctx* ctx, const rb200_model* model, const uint8_t* in, size_t n, uint32_t chunk_syms, uint8_t* blob,
+                size_t blob_cap, uint64_t* offsets, size_t* blob_size)
+{
+    const size_t n_chunks = rb200_chunk_count(n, chunk_syms);
+    if (n == 0) {
+        offsets[0] = 0;
+        if (blob_size) *blob_size = 0;
+        return RB200_OK;
+    }
+    const size_t slice = slice_symbols(n, chunk_syms);
+    const size_t n_slices = (n + slice - 1) / slice;
+    const size_t chunks_per_slice = slice / chunk_syms;
+    const size_t slice_bound = rb200_encode_bound(slice, chunk_syms);
+    int rc = reserve(ctx, ctx->st_in, n + 16);
+    if (rc == RB200_OK) rc = reserve(ctx, ctx->st_blob, n_slices * slice_bound + 16);
+    if (rc == RB200_OK) rc = reserve(ctx, ctx->st_offsets, n_slices * (chunks_per_slice + 1) * sizeof(uint64_t));
+    if (rc != RB200_OK) return rc;
+    uint8_t* d_in = static_cast<uint8_t*>(ctx->st_in.p);
+    uint8_t* d_blob = static_cast<uint8_t*>(ctx->st_blob.p);
+    uint64_t* d_off = static_cast<uint64_t*>(ctx->st_offsets.p);
+
+    RB_CUDA(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));       // staging buffers may still be in use upstream
+    RB_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_start, 0));
+    RB_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_start, 0));
+
+    auto issue = [&](size_t i) -> int {      // H2D + kernels for slice i
+        const size_t lo = i * slice, len = (n - lo < slice) ? n - lo : slice;
+        RB_CUDA(ctx, cudaMemcpyAsync(d_in + lo, in + lo, len, cudaMemcpyHostToDevice, ctx->s_in));
+        RB_CUDA(ctx, cudaEventRecord(ctx->ev_in[i], ctx->s_in));
+        RB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[i], 0));
+        uint64_t* so = d_off + i * (chunks_per_slice + 1);
+        int r = encode_device(ctx, model, d_in + lo, len, chunk_syms, d_blob + i * slice_bound, slice_bound, so);
+        if (r != RB200_OK) return r;
+        const size_t cnt = rb200_chunk_count(len, chunk_syms);
+        RB_CUDA(ctx, cudaMemcpyAsync(&ctx->h_slice_total[i], so + cnt, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        RB_CUDA(ctx, cudaEventRecord(ctx->ev_done[i], ctx->stream));
+        return RB200_OK;
+    };
+
+    rc = issue(0);
+    if (rc != RB200_OK) return rc;
+    size_t base = 0;
+    bool overflow = false;
+    for (size_t i = 0; i < n_slices; i++) {
+        if (i + 1 < n_slices) {
+            rc = issue(i + 1);
+            if (rc != RB200_OK) return rc;
+        }
+        RB_CUDA(ctx, cudaEventSynchronize(ctx->ev_done[i]));          // slice i's size is now on the host
+        const size_t total = static_cast<size_t>(ctx->h_slice_total[i]);
+        const size_t lo = i * slice, len = (n - lo < slice) ? n - lo : slice;
+        const size_t cnt = rb200_chunk_count(len, chunk_syms), c0 = i * chunks_per_slice;
+        if (base + total > blob_cap) {
+            overflow = true;
+        } else if (!overflow) {
+            RB_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_done[i], 0));
+            RB_CUDA(ctx, cudaMemcpyAsync(blob + base, d_blob + i * slice_bound, total, cudaMemcpyDeviceToHost, ctx->s_out));
+            RB_CUDA(ctx, cudaMemcpyAsync(offsets + c0, d_off + i * (chunks_per_slice + 1), cnt * sizeof(uint64_t),
+                                         cudaMemcpyDeviceToHost, ctx->s_out));
+        }
+        ctx->h_slice_total[i] = base;                                 // reuse as "base of slice i"
+        base += total;
+    }
+    RB_CUDA(ctx, cudaEventRecord(ctx->ev_out, ctx->s_out));
+    RB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_out, 0));
+    rc = rb200_sync(ctx);
+    if (rc != RB200_OK) return rc;
+    if (overflow) return RB200_E_SPACE;
+    for (size_t i = 1; i < n_slices; i++) {                           // rebase the directory
+        const uint64_t add = ctx->h_slice_total[i];
+        const size_t c0 = i * chunks_per_slice;
+        const size_t c1 = (c0 + chunks_per_slice < n_chunks) ? c0 + chunks_per_slice : n_chunks;
+        for (size_t c = c0; c < c1; c++) offsets[c] += add;
+    }
+    offsets[n_chunks] = base;
+    if (blob_size) *blob_size = base;
+    return RB200_OK;
+}
+
+// blob -> host buffers, overlapped the same way; no host synchronisation until the end because the
+// directory (and therefore every slice's byte range) is already on the host.
+int decode_host(rb200_ctx* ctx, const rb200_model* model, const uint8_t* blob, size_t blob_size, const uint64_t* offsets,
+                uint32_t chunk_syms, uint8_t* out, size_t n)
+{
+    const size_t n_chunks = rb200_chunk_count(n, chunk_syms);
+    if (n == 0) return RB200_OK;
+    if (offsets[n_chunks] != blob_size) return RB200_E_STREAM;
+    for (size_t c = 0; c < n_chunks; c++)                            // the copies below trust these
+        if (offsets[c] > offsets[c + 1] || offsets[c + 1] > blob_size) return RB200_E_STREAM;
+    const size_t slice = slice_symbols(n, chunk_syms);
+    const size_t n_slices = (n + slice - 1) / slice;
+    const size_t chunks_per_slice = slice / chunk_syms;
+    int rc = reserve(ctx, ctx->st_blob, blob_size + 16);
+    if (rc == RB200_OK) rc = reserve(ctx, ctx->st_offsets, (n_chunks + 1) * sizeof(uint64_t));
+    if (rc == RB200_OK) rc = reserve(ctx, ctx->st_out, n + 16);
+    if (rc != RB200_OK) return rc;
+    uint8_t* d_blob = static_cast<uint8_t*>(ctx->st_blob.p);
+    uint64_t* d_off = static_cast<uint64_t*>(ctx->st_offsets.p);
+    uint8_t* d_out = static_cast<uint8_t*>(ctx->st_out.p);
+
+    RB_CUDA(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
+    RB_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_start, 0));
+    RB_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_start, 0));
+    RB_CUDA(ctx, cudaMemcpyAsync(d_off, offsets, (n_chunks + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->s_in));
+    for (size_t i = 0; i < n_slices; i++) {
+        const size_t c0 = i * chunks_per_slice;
+        const size_t c1 = (c0 + chunks_per_slice < n_chunks) ? c0 + chunks_per_slice : n_chunks;
+        const size_t lo = i * slice, len = (n - lo < slice) ? n - lo : slice;
+        // bytes of chunks [c0, c1): from the (aligned) end of chunk c0-1 to the end of chunk c1-1
+        const size_t b0 = c0 ? static_cast<size_t>(offsets[c0] & ~15ull) : 0;
+        const size_t b1 = static_cast<size_t>(offsets[c1] & ~15ull);
+        if (b1 > b0) RB_CUDA(ctx, cudaMemcpyAsync(d_blob + b0, blob + b0, b1 - b0, cudaMemcpyHostToDevice, ctx->s_in));
+        RB_CUDA(ctx, cudaEventRecord(ctx->ev_in[i], ctx->s_in));
+        RB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[i], 0));
+        rc = decode_device(ctx, model, d_blob, blob_size, d_off + c0, chunk_syms, d_out + lo, len);
+        if (rc != RB200_OK) return rc;
+        RB_CUDA(ctx, cudaEventRecord(ctx->ev_done[i], ctx->stream));
+        RB_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_done[i], 0));
+        RB_CUDA(ctx, cudaMemcpyAsync(out + lo, d_out + lo, len, cudaMemcpyDeviceToHost, ctx->s_out));
+    }
+    RB_CUDA(ctx, cudaEventRecord(ctx->ev_out, ctx->s_out));
+    RB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_out, 0));
+    return rb200_sync(ctx);
+}
+
+}  // namespace
+
 extern "C" int rb200_encode(rb200_ctx* ctx, const rb200_model* model, const uint8_t* in, size_t n, uint32_t chunk_syms,
                             uint8_t* blob, size_t blob_cap, uint64_t* offsets, size_t* blob_size, int mem_kind)
 {
     if (!ctx || !model || model->ctx != ctx || !blob || !offsets || (!in && n) || !chunk_ok(chunk_syms)) return RB200_E_ARG;
     DeviceGuard g(ctx->device);
-    const size_t n_chunks = rb200_chunk_count(n, chunk_syms);
     if (mem_kind == RB200_MEM_DEVICE) {
         if (!aligned16(blob) || (reinterpret_cast<uintptr_t>(offsets) & 7)) return RB200_E_ARG;
         return encode_device(ctx, model, in, n, chunk_syms, blob, blob_cap, offsets);
     }
     if (mem_kind != RB200_MEM_HOST) return RB200_E_ARG;
-    // host buffers: stage in, run, stage out; synchronous like the reference's loops
-    const size_t bound = rb200_encode_bound(n, chunk_syms);
-    const size_t dev_cap = bound;   // the staging blob is always worst-case sized; blob_cap is checked after the directory is known
-    int rc = reserve(ctx, ctx->st_in, n + 16);
-    if (rc == RB200_OK) rc = reserve(ctx, ctx->st_blob, bound + 16);
-    if (rc == RB200_OK) rc = reserve(ctx, ctx->st_offsets, (n_chunks + 1) * sizeof(uint64_t));
-    if (rc != RB200_OK) return rc;
-    uint8_t* d_in = static_cast<uint8_t*>(ctx->st_in.p);
-    uint8_t* d_blob = static_cast<uint8_t*>(ctx->st_blob.p);
-    uint64_t* d_off = static_cast<uint64_t*>(ctx->st_offsets.p);
-    if (n) RB_CUDA(ctx, cudaMemcpyAsync(d_in, in, n, cudaMemcpyHostToDevice, ctx->stream));
-    rc = encode_device(ctx, model, d_in, n, chunk_syms, d_blob, dev_cap, d_off);
-    if (rc != RB200_OK) return rc;
-    RB_CUDA(ctx, cudaMemcpyAsync(offsets, d_off, (n_chunks + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    rc = rb200_sync(ctx);
-    if (rc != RB200_OK) return rc;
-    const size_t total = static_cast<size_t>(offsets[n_chunks]);
-    if (total > blob_cap) return RB200_E_SPACE;
-    if (total) RB_CUDA(ctx, cudaMemcpyAsync(blob, d_blob, total, cudaMemcpyDeviceToHost, ctx->stream));
-    RB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (blob_size) *blob_size = total;
-    return RB200_OK;
+    return encode_host(ctx, model, in, n, chunk_syms, blob, blob_cap, offsets, blob_size);
 }
 
 extern "C" int rb200_decode(rb200_ctx* ctx, const rb200_model* model, const uint8_t* blob, size_t blob_size,
@@ -448,26 +596,14 @@ extern "C" int rb200_decode(rb200_ctx* ctx, const rb200_model* model, const uint
     if (!ctx || !model || model->ctx != ctx || !offsets || (!out && n) || (!blob && blob_size) || !chunk_ok(chunk_syms))
         return RB200_E_ARG;
     if (blob_size & 15) return RB200_E_ARG;     // container invariant: the blob ends on a 16-byte boundary
+    if (blob_size >> 36) return RB200_E_ARG;    // the decoders index the blob in 16-byte vectors with 32 bits
     DeviceGuard g(ctx->device);
-    const size_t n_chunks = rb200_chunk_count(n, chunk_syms);
     if (mem_kind == RB200_MEM_DEVICE) {
         if (!aligned16(blob) || (reinterpret_cast<uintptr_t>(offsets) & 7)) return RB200_E_ARG;
         return decode_device(ctx, model, blob, blob_size, offsets, chunk_syms, out, n);
     }
     if (mem_kind != RB200_MEM_HOST) return RB200_E_ARG;
-    int rc = reserve(ctx, ctx->st_blob, blob_size + 16);
-    if (rc == RB200_OK) rc = reserve(ctx, ctx->st_offsets, (n_chunks + 1) * sizeof(uint64_t));
-    if (rc == RB200_OK) rc = reserve(ctx, ctx->st_out, n + 16);
-    if (rc != RB200_OK) return rc;
-    uint8_t* d_blob = static_cast<uint8_t*>(ctx->st_blob.p);
-    uint64_t* d_off = static_cast<uint64_t*>(ctx->st_offsets.p);
-    uint8_t* d_out = static_cast<uint8_t*>(ctx->st_out.p);
-    if (blob_size) RB_CUDA(ctx, cudaMemcpyAsync(d_blob, blob, blob_size, cudaMemcpyHostToDevice, ctx->stream));
-    RB_CUDA(ctx, cudaMemcpyAsync(d_off, offsets, (n_chunks + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
-    rc = decode_device(ctx, model, d_blob, blob_size, d_off, chunk_syms, d_out, n);
-    if (rc != RB200_OK) return rc;
-    if (n) RB_CUDA(ctx, cudaMemcpyAsync(out, d_out, n, cudaMemcpyDeviceToHost, ctx->stream));
-    return rb200_sync(ctx);
+    return decode_host(ctx, model, blob, blob_size, offsets, chunk_syms, out, n);
 }
 
 // ---------------------------------------------------------------------------

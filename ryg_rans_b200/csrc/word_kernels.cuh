@@ -31,15 +31,16 @@ constexpr uint32_t kUnitBytes = 512;
 struct StreamWindow {
     uint32_t ring;          // shared-space address of this warp's ring, 1 KiB aligned
     uint32_t fill_end;      // low 32 bits of the absolute blob byte offset filled so far
-    const uint4* next;      // this lane's 16 B of the next unit to fetch
-    const uint4* limit;     // end of blob (exclusive)
+    uint32_t next_vec;      // this lane's 16-byte vector of the next unit to fetch (index into the blob)
+    uint32_t limit_vec;     // blob_size / 16 (the C-ABI rejects blobs of 64 GiB and more)
+    const uint4* base;      // blob, warp-uniform
     uint4 parked;           // unit in flight
 
     __device__ __forceinline__ uint4 fetch()
     {
         uint4 v = make_uint4(0, 0, 0, 0);
-        if (next < limit) v = ldg_stream_u128(next);
-        next += 32;
+        if (next_vec < limit_vec) v = ldg_stream_u128(base + next_vec);
+        next_vec += 32;
         return v;
     }
 
@@ -47,15 +48,16 @@ struct StreamWindow {
     __device__ __forceinline__ void open(const uint8_t* blob, uint64_t blob_size, uint64_t off, uint32_t ring_addr, uint32_t lane)
     {
         ring = ring_addr;
-        const uint64_t unit0 = off / kUnitBytes;
-        next = reinterpret_cast<const uint4*>(blob) + unit0 * 32 + lane;
-        limit = reinterpret_cast<const uint4*>(blob) + blob_size / 16;
+        base = reinterpret_cast<const uint4*>(blob);
+        const uint32_t unit0 = static_cast<uint32_t>(off / kUnitBytes);
+        next_vec = unit0 * 32 + lane;
+        limit_vec = static_cast<uint32_t>(blob_size / 16);
         uint4 a = fetch();
         uint4 b = fetch();
         parked = fetch();
-        sts_u128(ring + (static_cast<uint32_t>(unit0 & 1) * kUnitBytes) + lane * 16, a);
-        sts_u128(ring + (static_cast<uint32_t>((unit0 + 1) & 1) * kUnitBytes) + lane * 16, b);
-        fill_end = static_cast<uint32_t>((unit0 + 2) * kUnitBytes);
+        sts_u128(ring + ((unit0 & 1) * kUnitBytes) + lane * 16, a);
+        sts_u128(ring + (((unit0 + 1) & 1) * kUnitBytes) + lane * 16, b);
+        fill_end = (unit0 + 2) * kUnitBytes;
         __syncwarp();
     }
 
@@ -132,13 +134,27 @@ __device__ __forceinline__ void word_decode_chunk(const uint8_t* __restrict__ bl
     uint8_t* o = chunk_out + lane;
     const uint32_t steps = m >> 5, rem = m & 31;
     uint32_t g = 0;
-    for (; g + 4 <= steps; g += 4) {
+    for (; g + 8 <= steps; g += 8) {
+        win.top_up(cursor, lane);
+        word_dec_step<WIDE>(x, cursor, tab, win.ring, o, lt, true);
+        word_dec_step<WIDE>(x, cursor, tab, win.ring, o + 32, lt, true);
+        word_dec_step<WIDE>(x, cursor, tab, win.ring, o + 64, lt, true);
+        word_dec_step<WIDE>(x, cursor, tab, win.ring, o + 96, lt, true);
+        win.top_up(cursor, lane);
+        word_dec_step<WIDE>(x, cursor, tab, win.ring, o + 128, lt, true);
+        word_dec_step<WIDE>(x, cursor, tab, win.ring, o + 160, lt, true);
+        word_dec_step<WIDE>(x, cursor, tab, win.ring, o + 192, lt, true);
+        word_dec_step<WIDE>(x, cursor, tab, win.ring, o + 224, lt, true);
+        o += 256;
+    }
+    if (g + 4 <= steps) {
         win.top_up(cursor, lane);
         word_dec_step<WIDE>(x, cursor, tab, win.ring, o, lt, true);
         word_dec_step<WIDE>(x, cursor, tab, win.ring, o + 32, lt, true);
         word_dec_step<WIDE>(x, cursor, tab, win.ring, o + 64, lt, true);
         word_dec_step<WIDE>(x, cursor, tab, win.ring, o + 96, lt, true);
         o += 128;
+        g += 4;
     }
     win.top_up(cursor, lane);
     for (; g < steps; g++) {
@@ -328,7 +344,10 @@ __device__ __forceinline__ void word_encode_chunk(const uint8_t* __restrict__ ch
     if (__any_sync(0xffffffffu, (st.flags & kWordSlots) != 0) && lane == 0) atomicOr(status, kStatSymbol);
 }
 
-__global__ void __launch_bounds__(kEncWarps * 32, 3)
+#ifndef RB200_ENC_MINBLOCKS
+#define RB200_ENC_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(kEncWarps * 32, RB200_ENC_MINBLOCKS)
 word_encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_syms, uint32_t n_chunks,
                    const WordEncEntry* __restrict__ g_table, uint8_t* __restrict__ scratch, uint32_t slot_bytes,
                    uint32_t* __restrict__ sizes, uint32_t* __restrict__ status)
