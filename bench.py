@@ -34,8 +34,10 @@ WORKLOADS = {
     # name: (coder, scale_bits, generator)
     "uniform_1GiB_word32": ("word", 12, "uniform"),
     "zipf1.1_1GiB_alias32": ("alias", 16, "zipf"),
-    "text_1GiB_word32": ("word", 12, "text"),
+    "text_1GiB_word32": ("word", 12, "text"),            # BASELINE configs[3] = this at --gpus 8 (8 x 1 GiB shards)
+    "blocks_64KiB_word32": ("blocks", 12, "blocks"),     # BASELINE configs[4]: 64 KiB blocks, one model per block
 }
+BLOCK_SIZE = 65536
 
 
 def parse_args():
@@ -62,6 +64,20 @@ def synth_torch(kind, n, seed, device):
     g.manual_seed(0x5EED0000 + seed)
     if kind == "uniform":
         return torch.randint(0, 256, (n,), dtype=torch.uint8, device=device, generator=g)
+    if kind == "blocks":
+        # every 64 KiB block has its own distribution: Zipf ranks pushed through a per-block permutation
+        nb = n // BLOCK_SIZE
+        p = 1.0 / torch.arange(1, 257, dtype=torch.float64) ** 1.3
+        cdf = torch.cumsum(p / p.sum(), 0).to(device=device, dtype=torch.float32)
+        out = torch.empty(n, dtype=torch.uint8, device=device)
+        perms = torch.argsort(torch.rand(nb, 256, device=device, generator=g), dim=1).to(torch.uint8)
+        step_blocks = 1024
+        for b0 in range(0, nb, step_blocks):
+            b1 = min(nb, b0 + step_blocks)
+            u = torch.rand((b1 - b0) * BLOCK_SIZE, device=device, generator=g)
+            ranks = torch.searchsorted(cdf, u).clamp_(max=255).view(b1 - b0, BLOCK_SIZE)
+            out[b0 * BLOCK_SIZE:b1 * BLOCK_SIZE] = torch.gather(perms[b0:b1], 1, ranks).reshape(-1)
+        return out
     if kind == "zipf":
         p = 1.0 / torch.arange(1, 257, dtype=torch.float64) ** 1.1
     elif kind == "text":
@@ -233,28 +249,49 @@ def run_ours(args, rank, local_rank, world):
     coder_name, sb, kind = WORKLOADS[args.workload]
     coder = rb.CODER_ALIAS if coder_name == "alias" else rb.CODER_WORD
     n, chunk = args.size, args.chunk
+    if coder_name == "blocks" and BLOCK_SIZE % chunk:
+        raise SystemExit("--chunk must divide the 64 KiB block size")
     stream = torch.cuda.current_stream()
     ctx = rb.Context(local_rank, stream.cuda_stream)
 
+    blocks = coder_name == "blocks"
+    if blocks:
+        n = (n // BLOCK_SIZE) * BLOCK_SIZE if n >= BLOCK_SIZE else BLOCK_SIZE
+        if args.size == 1 << 30:
+            n = 8192 * BLOCK_SIZE                      # 64 Ki blocks over 8 GPUs = 8192 blocks (512 MiB) per GPU
     data = synth_torch(kind, n, seed=rank, device=dev)
-    # model: device histogram -> host normalisation (reference order-dependent code stays on the host)
-    counts = ctx.histogram_device(data.data_ptr(), n)
-    st = rb.SymbolStats()
-    st.freqs[:] = counts.astype(np.uint32)
-    st.normalize_freqs(1 << sb)
-    model = ctx.model(coder, sb, st.freqs)
-
     n_chunks = ctx.chunk_count(n, chunk)
     cap = ctx.encode_bound(n, chunk)
     blob = torch.empty(cap, dtype=torch.uint8, device=dev)
     offsets = torch.zeros(n_chunks + 1, dtype=torch.int64, device=dev)
     out = torch.empty(n, dtype=torch.uint8, device=dev)
+    model_bytes = 0
+    if blocks:
+        n_blocks = n // BLOCK_SIZE
+        bfreqs = torch.zeros(n_blocks * 256, dtype=torch.int16, device=dev)
+        model_bytes = 512 * n_blocks                  # the per-block frequency tables travel with the blob
 
-    def enc():
-        ctx.encode_device(model, data.data_ptr(), n, chunk, blob.data_ptr(), cap, offsets.data_ptr())
+        def enc():                                    # per-block models are part of encoding a block
+            ctx.blocks_build_models_device(data.data_ptr(), n_blocks, BLOCK_SIZE, bfreqs.data_ptr())
+            ctx.blocks_encode_device(data.data_ptr(), n_blocks, BLOCK_SIZE, bfreqs.data_ptr(), chunk, blob.data_ptr(), cap,
+                                     offsets.data_ptr())
 
-    def dec(blob_size):
-        ctx.decode_device(model, blob.data_ptr(), blob_size, offsets.data_ptr(), chunk, out.data_ptr(), n)
+        def dec(blob_size):
+            ctx.blocks_decode_device(blob.data_ptr(), blob_size, offsets.data_ptr(), bfreqs.data_ptr(), n_blocks, BLOCK_SIZE, chunk,
+                                     out.data_ptr())
+    else:
+        # model: device histogram -> host normalisation (reference order-dependent code stays on the host)
+        counts = ctx.histogram_device(data.data_ptr(), n)
+        st = rb.SymbolStats()
+        st.freqs[:] = counts.astype(np.uint32)
+        st.normalize_freqs(1 << sb)
+        model = ctx.model(coder, sb, st.freqs)
+
+        def enc():
+            ctx.encode_device(model, data.data_ptr(), n, chunk, blob.data_ptr(), cap, offsets.data_ptr())
+
+        def dec(blob_size):
+            ctx.decode_device(model, blob.data_ptr(), blob_size, offsets.data_ptr(), chunk, out.data_ptr(), n)
 
     # warm-up + bit-exact verification (outside the timed region)
     enc()
@@ -319,7 +356,7 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- e2e: host pointers through the C-ABI, copies inside the timed region
     e2e = None
-    if args.e2e_steps > 0:
+    if args.e2e_steps > 0 and not blocks:
         h_in = torch.empty(n, dtype=torch.uint8).pin_memory()
         h_in.copy_(data)
         h_blob = torch.empty(cap, dtype=torch.uint8).pin_memory()
@@ -358,7 +395,7 @@ def run_ours(args, rank, local_rank, world):
             dist.destroy_process_group()
         return
     peak, peak_src = measured_peak()
-    algo_bytes = n + blob_size                       # (1 + c) bytes per symbol
+    algo_bytes = n + blob_size + model_bytes         # (1 + c) bytes per symbol (+ 512 B per block model)
     dec_gbs = algo_bytes / (dec_ms_max * 1e-3) / 1e9
     enc_gbs = algo_bytes / (enc_ms_max * 1e-3) / 1e9
     value = world * n * args.steps / (total_ms * 1e-3) / 1e9
@@ -369,10 +406,11 @@ def run_ours(args, rank, local_rank, world):
         "config": {"workload": args.workload, "symbols_per_gpu": n, "chunk_syms": chunk, "lanes": 32, "coder": coder_name,
                    "scale_bits": sb, "compressed_bytes_per_symbol": blob_size / n,
                    "l2": "inputs (1 GiB symbols + ~1 GiB blob) exceed the 126 MB L2; no flush needed",
-                   "step": "encode (3 launches) + decode (1 launch), device-resident"},
+                   "step": ("per-block models (1 launch) + " if blocks else "") + "encode (3 launches) + decode (1 launch), device-resident"},
         "decode_gsym_s": world * n / (dec_ms_max * 1e-3) / 1e9, "encode_gsym_s": world * n / (enc_ms_max * 1e-3) / 1e9,
         "decode_ms": dec_ms_max, "encode_ms": enc_ms_max,
-        "roofline": {"kernel": "word_decode_kernel" if coder_name == "word" else "alias_decode_kernel", "bound": "hbm",
+        "roofline": {"kernel": {"word": "word_decode_kernel", "alias": "alias_decode_kernel", "blocks": "block_decode_kernel"}[coder_name],
+                     "bound": "hbm",
                      "achieved": dec_gbs, "peak": peak, "unit": "GB/s", "frac": dec_gbs / peak, "traffic": None,
                      "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src},
         "roofline_encode_call": {"kernels": "encode + directory_scan + compact", "bound": "hbm", "achieved": enc_gbs, "peak": peak,
@@ -383,7 +421,8 @@ def run_ours(args, rank, local_rank, world):
         line["nccl_blob_gather_ms"] = gather_ms
     if world == 1 and not args.no_cpu_baseline:
         try:
-            line["cpu_baseline"] = cpu_reference_run(kind, coder_name, sb, min(args.cpu_sample, n), runs=2, threads=os.cpu_count() or 1)
+            line["cpu_baseline"] = cpu_reference_run("zipf" if blocks else kind, "word" if blocks else coder_name, sb,
+                                                     min(args.cpu_sample, n), runs=2, threads=os.cpu_count() or 1)
         except Exception as e:  # the baseline must not take the GPU number down with it
             line["cpu_baseline"] = {"error": repr(e)}
     print(json.dumps(line), flush=True)

@@ -208,7 +208,19 @@ class Context:
         self.lib.check(self.lib.dll.rb200_histogram(self.h, ptr, n, counts.ctypes.data_as(_u64p), MEM_DEVICE), self.h)
         return counts
 
-    # ---- per-block models
+    # ---- per-block models, device pointers (asynchronous)
+    def blocks_build_models_device(self, in_ptr, n_blocks, block_size, freqs_ptr):
+        self.lib.check(self.lib.dll.rb200_blocks_build_models(self.h, in_ptr, n_blocks, block_size, freqs_ptr, MEM_DEVICE), self.h)
+
+    def blocks_encode_device(self, in_ptr, n_blocks, block_size, freqs_ptr, chunk_syms, blob_ptr, blob_cap, offsets_ptr):
+        self.lib.check(self.lib.dll.rb200_blocks_encode(self.h, in_ptr, n_blocks, block_size, freqs_ptr, chunk_syms, blob_ptr,
+                                                        blob_cap, offsets_ptr, None, MEM_DEVICE), self.h)
+
+    def blocks_decode_device(self, blob_ptr, blob_size, offsets_ptr, freqs_ptr, n_blocks, block_size, chunk_syms, out_ptr):
+        self.lib.check(self.lib.dll.rb200_blocks_decode(self.h, blob_ptr, blob_size, offsets_ptr, freqs_ptr, n_blocks, block_size,
+                                                        chunk_syms, out_ptr, MEM_DEVICE), self.h)
+
+    # ---- per-block models, host buffers
     def blocks_build_models(self, data, n_blocks, block_size):
         data = np.ascontiguousarray(data, dtype=np.uint8)
         freqs = np.zeros((n_blocks, 256), np.uint16)

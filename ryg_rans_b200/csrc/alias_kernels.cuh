@@ -18,46 +18,52 @@
 namespace rb200 {
 
 constexpr uint32_t kByteL = 1u << 23;   // RANS_BYTE_L, rans_byte.h:50
-constexpr int kAliasDecWarps = 8;
-constexpr int kAliasEncWarps = 8;
+constexpr int kAliasDecWarps = 16;
+constexpr uint32_t kAliasDecReplicas = 8;    // quarter-warp lanes hit 8 different 16-byte bank groups
 
-// RansDecGetAlias (main_alias.cpp:252-267) + RansDecRenorm (rans_byte.h:307-318), warp-wide
-__device__ __forceinline__ void alias_dec_step(uint32_t& x, uint32_t& cursor, uint32_t div_tab, uint32_t dec_tab,
-                                               uint32_t ring, uint8_t* o, uint32_t lt, uint32_t sb, bool active)
+// RansDecGetAlias (main_alias.cpp:252-267) + RansDecRenorm (rans_byte.h:307-318), warp-wide.
+// tab_lane = shared address of this lane's replica of the 256 x 16 B bucket table.
+__device__ __forceinline__ void alias_dec_step(uint32_t& x, uint32_t& cursor, uint32_t tab_lane, uint32_t ring, uint8_t* o,
+                                               uint32_t lt, uint32_t sb, bool active)
 {
     bool n1 = false, n2 = false;
     if (active) {
         const uint32_t xm = x & ((1u << sb) - 1);                          // :258
         const uint32_t bucket = xm >> (sb - 8);                            // :259
-        const uint32_t divider = lds_u32_ro(div_tab + 4u * bucket);
-        const uint32_t b2 = 2u * bucket + (xm < divider ? 1u : 0u);        // :260-262
-        const uint2 e = lds_u64_ro(dec_tab + 8u * b2);                     // {slot_freq | sym << 24, slot_adjust}
-        x = (e.x & 0xffffffu) * (x >> sb) + xm - e.y;                      // :265
-        *o = static_cast<uint8_t>(e.x >> 24);                              // :266
+        const uint4 e = lds_u128_ro(tab_lane + bucket * (kAliasDecReplicas * 16));
+        const bool own = xm < e.x;                                         // :261 (bucket2 = 2 * bucket + 1)
+        const uint32_t fs = own ? e.z : e.y;                               // slot_freqs | sym_id << 17
+        const uint32_t adj = own ? (e.w >> 16) : (e.w & 0xffffu);
+        x = (fs & 0x1ffffu) * (x >> sb) + ((xm - adj) & 0xffffu);          // :265
+        *o = static_cast<uint8_t>(fs >> 17);                               // :266
         n1 = x < kByteL;
         n2 = x < (kByteL >> 8);
     }
     const uint32_t m1 = __ballot_sync(0xffffffffu, n1);
     const uint32_t m2 = __ballot_sync(0xffffffffu, n2);
-    const uint32_t a = cursor + __popc(m1 & lt) + __popc(m2 & lt);
+    uint32_t a = cursor + __popc(m1 & lt);
+    if (m2) a += __popc(m2 & lt);                                          // warp-uniform: two-byte refills are rare
     const uint32_t b0 = lds_u8(ring | (a & (kRingBytes - 1)));
-    const uint32_t b1 = lds_u8(ring | ((a + 1) & (kRingBytes - 1)));
     if (n1) x = (x << 8) | b0;                                             // rans_byte.h:313
-    if (n2) x = (x << 8) | b1;
-    cursor += __popc(m1) + __popc(m2);
+    cursor += __popc(m1);
+    if (m2) {
+        const uint32_t b1 = lds_u8(ring | ((a + 1) & (kRingBytes - 1)));
+        if (n2) x = (x << 8) | b1;
+        cursor += __popc(m2);
+    }
 }
 
-__global__ void __launch_bounds__(kAliasDecWarps * 32, 8)
+__global__ void __launch_bounds__(kAliasDecWarps * 32, 4)
 alias_decode_kernel(const uint8_t* __restrict__ blob, uint64_t blob_size, const uint64_t* __restrict__ offsets, uint32_t sb,
-                    const uint32_t* __restrict__ g_divider, const AliasDecEntry* __restrict__ g_dec,
-                    uint8_t* __restrict__ out, uint64_t n, uint32_t chunk_syms, uint32_t n_chunks, uint32_t* __restrict__ status)
+                    const AliasDecEntry* __restrict__ g_dec, uint8_t* __restrict__ out, uint64_t n, uint32_t chunk_syms,
+                    uint32_t n_chunks, uint32_t* __restrict__ status)
 {
-    __shared__ __align__(16) uint32_t s_div[256];
-    __shared__ __align__(16) uint2 s_dec[512];
-    __shared__ __align__(1024) uint8_t s_ring[kAliasDecWarps][kRingBytes];
-
-    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_div[i] = g_divider[i];
-    for (uint32_t i = threadIdx.x; i < 512; i += blockDim.x) s_dec[i] = make_uint2(g_dec[i].freq_sym, g_dec[i].adjust);
+    extern __shared__ __align__(1024) uint8_t s_adec[];       // [16 x 1 KiB rings][32 KiB table]
+    uint4* s_tab = reinterpret_cast<uint4*>(s_adec + kAliasDecWarps * kRingBytes);
+    for (uint32_t i = threadIdx.x; i < 256 * kAliasDecReplicas; i += blockDim.x) {
+        const AliasDecEntry e = g_dec[i / kAliasDecReplicas];
+        s_tab[i] = make_uint4(e.divider, e.alt0, e.alt1, e.adjust);
+    }
     __syncthreads();
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -74,7 +80,7 @@ alias_decode_kernel(const uint8_t* __restrict__ blob, uint64_t blob_size, const 
     }
 
     StreamWindow win;
-    win.open(blob, blob_size, off, smem_addr(&s_ring[warp][0]), lane);
+    win.open(blob, blob_size, off, smem_addr(s_adec) + warp * kRingBytes, lane);
     uint32_t cursor = static_cast<uint32_t>(off);
     // RansDecInit x 32 (rans_byte.h:109-122)
     uint32_t x = 0;
@@ -83,139 +89,224 @@ alias_decode_kernel(const uint8_t* __restrict__ blob, uint64_t blob_size, const 
     cursor += kHeaderBytes;
 
     const uint32_t lt = lanemask_lt();
-    const uint32_t div_tab = smem_addr(s_div), dec_tab = smem_addr(s_dec);
+    const uint32_t tab_lane = smem_addr(s_tab) + (lane & (kAliasDecReplicas - 1)) * 16;
     uint8_t* o = out + first + lane;
     const uint32_t steps = m >> 5, rem = m & 31;
     uint32_t g = 0;
     for (; g + 4 <= steps; g += 4) {
         win.top_up(cursor, lane);
-        alias_dec_step(x, cursor, div_tab, dec_tab, win.ring, o, lt, sb, true);
-        alias_dec_step(x, cursor, div_tab, dec_tab, win.ring, o + 32, lt, sb, true);
-        alias_dec_step(x, cursor, div_tab, dec_tab, win.ring, o + 64, lt, sb, true);
-        alias_dec_step(x, cursor, div_tab, dec_tab, win.ring, o + 96, lt, sb, true);
+        alias_dec_step(x, cursor, tab_lane, win.ring, o, lt, sb, true);
+        alias_dec_step(x, cursor, tab_lane, win.ring, o + 32, lt, sb, true);
+        alias_dec_step(x, cursor, tab_lane, win.ring, o + 64, lt, sb, true);
+        alias_dec_step(x, cursor, tab_lane, win.ring, o + 96, lt, sb, true);
         o += 128;
     }
     win.top_up(cursor, lane);
     for (; g < steps; g++) {
-        alias_dec_step(x, cursor, div_tab, dec_tab, win.ring, o, lt, sb, true);
+        alias_dec_step(x, cursor, tab_lane, win.ring, o, lt, sb, true);
         o += 32;
     }
-    if (rem) alias_dec_step(x, cursor, div_tab, dec_tab, win.ring, o, lt, sb, lane < rem);
+    if (rem) alias_dec_step(x, cursor, tab_lane, win.ring, o, lt, sb, lane < rem);
 
     const bool bad = (cursor != static_cast<uint32_t>(end)) || (x != kByteL);
     if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(status, kStatStream);
 }
+constexpr uint32_t kAliasDecSmem = kAliasDecWarps * kRingBytes + 256 * kAliasDecReplicas * 16;   // 48 KiB
 
-// RansEncPutAlias (main_alias.cpp:241-250) = RansEncRenorm (rans_byte.h:62-74) + divide + remap gather
-__device__ __forceinline__ void alias_enc_step(uint32_t& x, uint32_t& emitted, uint32_t& flags, uint32_t sym, uint32_t tab,
-                                               const uint16_t* __restrict__ remap, uint8_t* slot_end, uint32_t gt, uint32_t sb,
-                                               bool active)
+// ---------------------------------------------------------------------------
+// K4: 32-way alias encode.  RansEncPutAlias (main_alias.cpp:241-250) = RansEncRenorm
+// (rans_byte.h:62-74) + divide + alias_remap gather.
+//
+// Persistent kernel, one 32-warp CTA per SM, because the encoder's slot permutation
+// alias_remap (u16, 2 << scale_bits bytes = 128 KiB at scale_bits 16) lives in
+// shared memory next to the 8x replicated per-symbol table ({magic, freq, cum, shift}, one
+// conflict-free LDS.128 per step) and the per-warp 512 B symbol stage + 512 B output ring
+// (same staged, vectorised I/O as the word encoder).
+// ---------------------------------------------------------------------------
+constexpr int kAliasEncWarps = 32;
+constexpr uint32_t kAliasEncFixedSmem = kAliasEncWarps * kEncWarpSmem + kEncTableBytes;   // 64 KiB + remap
+
+__device__ __forceinline__ uint32_t lds_u16_ro(uint32_t addr)
+{
+    uint16_t v;
+    asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
+}
+
+struct AliasEncState {
+    uint32_t x;        // rANS state
+    uint32_t wpos;     // un-wrapped ring position of the next byte = 511 - bytes_emitted
+    uint32_t flags;
+};
+
+__device__ __forceinline__ void alias_enc_step(AliasEncState& st, uint32_t sym, uint32_t tab_lane, uint32_t remap, uint32_t ring,
+                                               uint32_t gt, uint32_t sb, bool active)
 {
     bool n1 = false, n2 = false;
     uint4 e = make_uint4(0, 1, 0, 0);
     if (active) {
-        e = lds_u128_ro(tab + 16u * sym);                    // {magic, freq, cum, shift}
-        flags |= e.w;
-        const uint32_t x_max = e.y << (31 - sb);             // ((L >> sb) << 8) * freq, rans_byte.h:64
-        n1 = x >= x_max;                                     // :65
-        n2 = (x >> 8) >= x_max;                              // second trip of the do/while, :67-70
+        e = lds_u128_ro(tab_lane + sym * (kEncReplicas * 16));   // {magic, freq, cum, shift}
+        st.flags |= e.w;
+        const uint32_t x_max = e.y << (31 - sb);                  // ((L >> sb) << 8) * freq, rans_byte.h:64
+        n1 = st.x >= x_max;                                       // :65
+        n2 = (st.x >> 8) >= x_max;                                // second trip of the do/while, :67-70
     }
     const uint32_t m1 = __ballot_sync(0xffffffffu, n1);
     const uint32_t m2 = __ballot_sync(0xffffffffu, n2);
     if (n1) {
         // lanes are visited 31..0 (main_alias.cpp:365-370 generalised); each writes downwards
-        const uint32_t t = emitted + __popc(m1 & gt) + __popc(m2 & gt);
-        slot_end[-static_cast<int64_t>(t + 1)] = static_cast<uint8_t>(x);          // :68
-        if (n2) slot_end[-static_cast<int64_t>(t + 2)] = static_cast<uint8_t>(x >> 8);
-        x >>= n2 ? 16 : 8;                                                          // :69
+        const uint32_t pos = st.wpos - __popc(m1 & gt) - __popc(m2 & gt);
+        sts_u8(ring | (pos & (kEncRingBytes - 1)), st.x);                          // :68
+        if (n2) sts_u8(ring | ((pos - 1) & (kEncRingBytes - 1)), st.x >> 8);
+        st.x >>= n2 ? 16 : 8;                                                      // :69
     }
-    emitted += __popc(m1) + __popc(m2);
+    st.wpos -= __popc(m1) + __popc(m2);
     if (active) {
-        const uint32_t q = static_cast<uint32_t>((static_cast<uint64_t>(x) + __umulhi(x, e.x)) >> (e.w & 31u));   // x / freq
-        const uint32_t r = x - q * e.y;                                                                          // x % freq
-        x = (q << sb) + __ldg(remap + r + e.z);                                     // main_alias.cpp:249
+        const uint32_t hi = __umulhi(st.x, e.x);                                   // exact x / freq, as in the word encoder
+        const uint32_t lo = st.x + hi;
+        const uint32_t q = funnel_shr_wrap(lo, lo < hi ? 1u : 0u, e.w);
+        const uint32_t r = st.x - q * e.y;                                         // x % freq
+        st.x = (q << sb) + lds_u16_ro(remap + 2u * (r + e.z));                     // main_alias.cpp:249
     }
 }
 
-__global__ void __launch_bounds__(kAliasEncWarps * 32, 4)
+__device__ __forceinline__ void alias_encode_chunk(const uint8_t* __restrict__ chunk_in, uint32_t m, uint32_t chunk, uint32_t tab,
+                                                   uint32_t remap, uint32_t wsm, uint32_t sb, uint8_t* __restrict__ scratch,
+                                                   uint32_t slot_bytes, uint32_t* __restrict__ sizes, uint32_t* __restrict__ status)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t stage = wsm, ring = wsm + kEncStageBytes;
+    uint8_t* slot_end = scratch + static_cast<uint64_t>(chunk + 1) * slot_bytes;
+    const uint32_t tab_lane = tab + (lane & (kEncReplicas - 1)) * 16;
+    const uint32_t gt = lanemask_gt();
+
+    AliasEncState st;
+    st.x = kByteL;                              // RansEncInit, rans_byte.h:56-59
+    st.wpos = kEncRingBytes - 1;
+    st.flags = 0;
+    uint32_t flushed = 0;
+    const uint32_t steps = m >> 5, rem = m & 31;
+    const uint32_t nblk = steps >> 4;
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(chunk_in) & 15) == 0;
+
+    uint4 parked = make_uint4(0, 0, 0, 0);
+    if (nblk && vec_ok) parked = ldg_stream_u128(reinterpret_cast<const uint4*>(chunk_in + (nblk - 1) * kEncStageBytes) + lane);
+    if (rem) {
+        const bool active = lane < rem;
+        const uint32_t s = active ? chunk_in[static_cast<uint64_t>(steps) * 32 + lane] : 0;
+        alias_enc_step(st, s, tab_lane, remap, ring, gt, sb, active);
+    }
+    for (uint32_t g = steps; g > nblk * 16; g--) {
+        const uint32_t s = chunk_in[static_cast<uint64_t>(g - 1) * 32 + lane];
+        alias_enc_step(st, s, tab_lane, remap, ring, gt, sb, true);
+        if (((g - 1) & 3) == 0) word_enc_flush(kEncRingBytes - 1 - st.wpos, flushed, ring, slot_end, lane);
+    }
+    word_enc_flush(kEncRingBytes - 1 - st.wpos, flushed, ring, slot_end, lane);
+
+    for (uint32_t b = nblk; b-- > 0;) {
+        __syncwarp();
+        if (vec_ok) {
+            sts_u128(stage + lane * 16, parked);
+            if (b) parked = ldg_stream_u128(reinterpret_cast<const uint4*>(chunk_in + (b - 1) * kEncStageBytes) + lane);
+        } else {
+            const uint8_t* p = chunk_in + b * kEncStageBytes + lane;
+#pragma unroll
+            for (int j = 0; j < 16; j++) sts_u8(stage + j * 32 + lane, p[j * 32]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int grp = 3; grp >= 0; grp--) {
+#pragma unroll
+            for (int j = 3; j >= 0; j--)
+                alias_enc_step(st, lds_u8(stage + (grp * 4 + j) * 32 + lane), tab_lane, remap, ring, gt, sb, true);
+            if (kEncRingBytes - 1 - st.wpos - flushed >= 256) word_enc_flush(kEncRingBytes - 1 - st.wpos, flushed, ring, slot_end, lane);
+        }
+    }
+
+    // RansEncFlush for lanes 31..0 (rans_byte.h:93-105): lane 31's most significant byte is the first byte
+    // written (highest address); lane 0's least significant byte ends up first in memory
+    word_enc_flush(kEncRingBytes - 1 - st.wpos, flushed, ring, slot_end, lane);     // < 16 bytes stay pending
+    const uint32_t hpos = st.wpos - 4u * (31 - lane);
+#pragma unroll
+    for (int j = 0; j < 4; j++) sts_u8(ring | ((hpos - (3 - j)) & (kEncRingBytes - 1)), st.x >> (8 * j));
+    st.wpos -= kHeaderBytes;
+    const uint32_t produced = kEncRingBytes - 1 - st.wpos;
+    word_enc_flush(produced, flushed, ring, slot_end, lane);
+    const uint32_t left = produced - flushed;                        // < 16 bytes: head of the stream
+    if (lane < left) {
+        const uint32_t off = flushed + lane + 1;
+        *(slot_end - off) = static_cast<uint8_t>(lds_u8(ring | ((0u - off) & (kEncRingBytes - 1))));
+    }
+    if (lane == 0) sizes[chunk] = produced;
+    if (__any_sync(0xffffffffu, (st.flags & kEncBadSymbol) != 0) && lane == 0) atomicOr(status, kStatSymbol);
+}
+
+__global__ void __launch_bounds__(kAliasEncWarps * 32, 1)
 alias_encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_syms, uint32_t n_chunks, uint32_t sb,
-                    const AliasEncEntry* __restrict__ g_enc, const uint16_t* __restrict__ remap,
+                    const AliasEncEntry* __restrict__ g_enc, const uint16_t* __restrict__ g_remap,
                     uint8_t* __restrict__ scratch, uint32_t slot_bytes, uint32_t* __restrict__ sizes,
                     uint32_t* __restrict__ status)
 {
-    __shared__ __align__(16) uint4 s_enc[256];
-    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
-        const AliasEncEntry e = g_enc[i];
+    extern __shared__ __align__(1024) uint8_t s_alias[];      // [32 x 1 KiB stage+ring][32 KiB table][remap]
+    uint4* s_tab = reinterpret_cast<uint4*>(s_alias + kAliasEncWarps * kEncWarpSmem);
+    uint4* s_remap = reinterpret_cast<uint4*>(s_alias + kAliasEncFixedSmem);
+    for (uint32_t i = threadIdx.x; i < 256 * kEncReplicas; i += blockDim.x) {
+        const AliasEncEntry e = g_enc[i / kEncReplicas];
         // a symbol the model does not contain: keep the step well defined (freq 1), flag it
-        s_enc[i] = (e.shift & kEncBadSymbol) ? make_uint4(0, 1, 0, kEncBadSymbol) : make_uint4(e.magic, e.freq, e.cum, e.shift);
+        s_tab[i] = (e.shift & kEncBadSymbol) ? make_uint4(0, 1, 0, kEncBadSymbol) : make_uint4(e.magic, e.freq, e.cum, e.shift);
     }
+    const uint32_t remap_vecs = (2u << sb) / 16;
+    for (uint32_t i = threadIdx.x; i < remap_vecs; i += blockDim.x) s_remap[i] = reinterpret_cast<const uint4*>(g_remap)[i];
     __syncthreads();
 
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t chunk = blockIdx.x * kAliasEncWarps + warp;
-    if (chunk >= n_chunks) return;
-
-    const uint64_t first = static_cast<uint64_t>(chunk) * chunk_syms;
-    const uint32_t m = static_cast<uint32_t>(min(static_cast<uint64_t>(chunk_syms), n - first));
-    const uint8_t* src = in + first + lane;
-    uint8_t* slot_end = scratch + static_cast<uint64_t>(chunk + 1) * slot_bytes;
-    const uint32_t tab = smem_addr(s_enc);
-    const uint32_t gt = lanemask_gt();
-
-    uint32_t x = kByteL;                       // RansEncInit, rans_byte.h:56-59
-    uint32_t emitted = 0, flags = 0;
-    const uint32_t steps = m >> 5, rem = m & 31;
-    if (rem) {
-        const bool active = lane < rem;
-        const uint32_t s = active ? src[static_cast<uint64_t>(steps) * 32] : 0;
-        alias_enc_step(x, emitted, flags, s, tab, remap, slot_end, gt, sb, active);
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t base = smem_addr(s_alias);
+    for (uint32_t chunk = blockIdx.x * kAliasEncWarps + warp; chunk < n_chunks; chunk += gridDim.x * kAliasEncWarps) {
+        const uint64_t first = static_cast<uint64_t>(chunk) * chunk_syms;
+        const uint32_t m = static_cast<uint32_t>(min(static_cast<uint64_t>(chunk_syms), n - first));
+        alias_encode_chunk(in + first, m, chunk, base + kAliasEncWarps * kEncWarpSmem, base + kAliasEncFixedSmem,
+                           base + warp * kEncWarpSmem, sb, scratch, slot_bytes, sizes, status);
     }
-    uint32_t g = steps;
-    for (; g >= 4; g -= 4) {
-        const uint8_t* p = src + static_cast<uint64_t>(g - 4) * 32;
-        const uint32_t s3 = p[96], s2 = p[64], s1 = p[32], s0 = p[0];
-        alias_enc_step(x, emitted, flags, s3, tab, remap, slot_end, gt, sb, true);
-        alias_enc_step(x, emitted, flags, s2, tab, remap, slot_end, gt, sb, true);
-        alias_enc_step(x, emitted, flags, s1, tab, remap, slot_end, gt, sb, true);
-        alias_enc_step(x, emitted, flags, s0, tab, remap, slot_end, gt, sb, true);
-    }
-    for (; g >= 1; g--) {
-        const uint32_t s = src[static_cast<uint64_t>(g - 1) * 32];
-        alias_enc_step(x, emitted, flags, s, tab, remap, slot_end, gt, sb, true);
-    }
+}
 
-    // RansEncFlush for lanes 31..0 (rans_byte.h:93-105): 4 little-endian bytes per lane, lane 0 first
-    uint8_t* head = slot_end - emitted - kHeaderBytes + 4 * lane;
-    head[0] = static_cast<uint8_t>(x);
-    head[1] = static_cast<uint8_t>(x >> 8);
-    head[2] = static_cast<uint8_t>(x >> 16);
-    head[3] = static_cast<uint8_t>(x >> 24);
-    if (lane == 0) sizes[chunk] = kHeaderBytes + emitted;
-    if (__any_sync(0xffffffffu, (flags & kEncBadSymbol) != 0) && lane == 0) atomicOr(status, kStatSymbol);
+inline int alias_sm_count()
+{
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    return sms;
 }
 
 inline void configure_alias_kernels()
 {
     cudaFuncSetAttribute(alias_decode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(alias_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAliasDecSmem);
+    cudaFuncSetAttribute(alias_encode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(alias_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAliasEncFixedSmem + (2u << 16));
 }
 
 inline int launch_alias_encode(cudaStream_t stream, const uint8_t* d_in, uint64_t n, uint32_t chunk_syms, uint32_t n_chunks,
                                uint32_t sb, const AliasEncEntry* enc, const uint16_t* remap, uint8_t* scratch, uint32_t slot,
                                uint32_t* sizes, uint32_t* status)
 {
-    const uint32_t grid = (n_chunks + kAliasEncWarps - 1) / kAliasEncWarps;
-    alias_encode_kernel<<<grid, kAliasEncWarps * 32, 0, stream>>>(d_in, n, chunk_syms, n_chunks, sb, enc, remap, scratch, slot,
-                                                                   sizes, status);
+    uint32_t grid = (n_chunks + kAliasEncWarps - 1) / kAliasEncWarps;
+    const uint32_t sms = static_cast<uint32_t>(alias_sm_count());
+    if (grid > sms) grid = sms;                       // persistent: one CTA per SM, chunks strided over CTAs
+    alias_encode_kernel<<<grid, kAliasEncWarps * 32, kAliasEncFixedSmem + (2u << sb), stream>>>(d_in, n, chunk_syms, n_chunks, sb, enc,
+                                                                                                 remap, scratch, slot, sizes, status);
     return 0;
 }
 
 inline int launch_alias_decode(cudaStream_t stream, const uint8_t* blob, uint64_t blob_size, const uint64_t* offsets, uint32_t sb,
-                               const uint32_t* divider, const AliasDecEntry* dec, uint8_t* out, uint64_t n, uint32_t chunk_syms,
-                               uint32_t n_chunks, uint32_t* status)
+                               const AliasDecEntry* dec, uint8_t* out, uint64_t n, uint32_t chunk_syms, uint32_t n_chunks,
+                               uint32_t* status)
 {
     const uint32_t grid = (n_chunks + kAliasDecWarps - 1) / kAliasDecWarps;
-    alias_decode_kernel<<<grid, kAliasDecWarps * 32, 0, stream>>>(blob, blob_size, offsets, sb, divider, dec, out, n, chunk_syms,
-                                                                   n_chunks, status);
+    alias_decode_kernel<<<grid, kAliasDecWarps * 32, kAliasDecSmem, stream>>>(blob, blob_size, offsets, sb, dec, out, n, chunk_syms,
+                                                                              n_chunks, status);
     return 0;
 }
 

@@ -222,17 +222,23 @@ block_decode_kernel(const uint8_t* __restrict__ blob, uint64_t blob_size, const 
         if (tid == 0) atomicOr(status, kStatStream);
         return;
     }
-    // RansWordTablesInitSymbol for every slot (rans_word_sse41.h:64-72): slot -> symbol by
-    // binary search over the cumulative table, so the work is balanced however skewed the model
-    for (uint32_t slot = tid; slot < kWordSlots; slot += blockDim.x) {
-        uint32_t lo = 0, hi = 256;                               // largest s with cum[s] <= slot and freq > 0
+    // RansWordTablesInitSymbol for every slot (rans_word_sse41.h:64-72).  Each thread owns a run of
+    // consecutive slots: one binary search over the cumulative table for the first, then it walks
+    // forward, so the work is balanced however skewed the model is.
+    {
+        const uint32_t per = kWordSlots / blockDim.x;            // blockDim is a power of two between 128 and 1024
+        uint32_t slot = tid * per;
+        uint32_t lo = 0, hi = 256;                               // largest s with cum[s] <= slot
         while (hi - lo > 1) {
             const uint32_t mid = (lo + hi) >> 1;
             if (s_cum[mid] <= slot) lo = mid; else hi = mid;
         }
-        const uint32_t f = s_cum[lo + 1] - s_cum[lo];
-        if (f == kWordSlots) s_flag[1] = 1;
-        s_tab[slot] = ((f & 0xfffu) << 20) | ((slot - s_cum[lo]) << 8) | lo;
+        for (uint32_t j = 0; j < per; j++, slot++) {
+            while (slot >= s_cum[lo + 1]) lo++;                  // also steps over zero-width symbols
+            const uint32_t f = s_cum[lo + 1] - s_cum[lo];
+            if (f == kWordSlots) s_flag[1] = 1;
+            s_tab[slot] = ((f & 0xfffu) << 20) | ((slot - s_cum[lo]) << 8) | lo;
+        }
     }
     __syncthreads();
 
@@ -284,8 +290,8 @@ block_encode_kernel(const uint8_t* __restrict__ in, uint32_t block_size, const u
 
 inline uint32_t block_threads(uint32_t block_size, uint32_t chunk_syms)
 {
-    uint32_t warps = block_size / chunk_syms;
-    if (warps < 4) warps = 4;          // table construction wants a few warps even for 1-chunk blocks
+    uint32_t warps = 4;                // table construction wants a few warps even for 1-chunk blocks;
+    while (warps < block_size / chunk_syms) warps <<= 1;   // power of two so 4096 slots split evenly
     return warps * 32;
 }
 

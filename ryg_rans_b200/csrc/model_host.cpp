@@ -203,9 +203,10 @@ int build_alias_device_tables(const uint32_t freqs[256], uint32_t scale_bits, Al
     int rc = rb200_alias_tables_build(freqs, cum, divider, slot_adjust, slot_freqs, sym_id, remap.data());
     if (rc != RB200_OK) return rc;
     t.scale_bits = scale_bits;
-    for (int b = 0; b < 256; b++) t.divider[b] = divider[b];
-    for (int i = 0; i < 512; i++)
-        t.dec[i] = {slot_freqs[i] | (static_cast<uint32_t>(sym_id[i]) << 24), slot_adjust[i]};
+    for (int b = 0; b < 256; b++)
+        t.dec[b] = {divider[b], slot_freqs[2 * b] | (static_cast<uint32_t>(sym_id[2 * b]) << 17),
+                    slot_freqs[2 * b + 1] | (static_cast<uint32_t>(sym_id[2 * b + 1]) << 17),
+                    (slot_adjust[2 * b] & 0xffffu) | (slot_adjust[2 * b + 1] << 16)};
     t.remap.resize(cum[256]);
     for (uint32_t i = 0; i < cum[256]; i++) t.remap[i] = static_cast<uint16_t>(remap[i]);
     for (int s = 0; s < 256; s++) {

@@ -56,8 +56,7 @@ struct rb200_model {
     int wide = 0;
     uint32_t* d_word_dec = nullptr;          // 4096 x u32
     WordEncEntry* d_word_enc = nullptr;      // 256
-    uint32_t* d_alias_divider = nullptr;     // 256
-    AliasDecEntry* d_alias_dec = nullptr;    // 512
+    AliasDecEntry* d_alias_dec = nullptr;    // 256 x 16 B
     AliasEncEntry* d_alias_enc = nullptr;    // 256
     uint16_t* d_alias_remap = nullptr;       // 1 << scale_bits
 };
@@ -256,7 +255,7 @@ extern "C" void rb200_model_destroy(rb200_model* m)
     DeviceGuard g(m->ctx->device);
     cudaStreamSynchronize(m->ctx->stream);
     cudaFree(m->d_word_dec); cudaFree(m->d_word_enc);
-    cudaFree(m->d_alias_divider); cudaFree(m->d_alias_dec); cudaFree(m->d_alias_enc); cudaFree(m->d_alias_remap);
+    cudaFree(m->d_alias_dec); cudaFree(m->d_alias_enc); cudaFree(m->d_alias_remap);
     delete m;
 }
 
@@ -291,11 +290,9 @@ extern "C" int rb200_model_create(rb200_ctx* ctx, int coder, uint32_t scale_bits
         rc = build_alias_device_tables(freqs, scale_bits, *t);
         if (rc == RB200_OK) {
             const size_t remap_bytes = t->remap.size() * sizeof(uint16_t);
-            e = cudaMalloc(&m->d_alias_divider, sizeof t->divider);
-            if (e == cudaSuccess) e = cudaMalloc(&m->d_alias_dec, sizeof t->dec);
+            e = cudaMalloc(&m->d_alias_dec, sizeof t->dec);
             if (e == cudaSuccess) e = cudaMalloc(&m->d_alias_enc, sizeof t->enc);
             if (e == cudaSuccess) e = cudaMalloc(&m->d_alias_remap, remap_bytes);
-            if (e == cudaSuccess) e = cudaMemcpy(m->d_alias_divider, t->divider, sizeof t->divider, cudaMemcpyHostToDevice);
             if (e == cudaSuccess) e = cudaMemcpy(m->d_alias_dec, t->dec, sizeof t->dec, cudaMemcpyHostToDevice);
             if (e == cudaSuccess) e = cudaMemcpy(m->d_alias_enc, t->enc, sizeof t->enc, cudaMemcpyHostToDevice);
             if (e == cudaSuccess) e = cudaMemcpy(m->d_alias_remap, t->remap.data(), remap_bytes, cudaMemcpyHostToDevice);
@@ -425,8 +422,8 @@ int decode_device(rb200_ctx* ctx, const rb200_model* model, const uint8_t* d_blo
                                                                                  n, chunk_syms, n_chunks, ctx->d_status);
         return check_launch(ctx, "word_decode_kernel");
     }
-    int rc = launch_alias_decode(ctx->stream, d_blob, blob_size, d_offsets, model->scale_bits, model->d_alias_divider,
-                                 model->d_alias_dec, d_out, n, chunk_syms, n_chunks, ctx->d_status);
+    int rc = launch_alias_decode(ctx->stream, d_blob, blob_size, d_offsets, model->scale_bits, model->d_alias_dec, d_out, n,
+                                 chunk_syms, n_chunks, ctx->d_status);
     if (rc == RB200_OK) rc = check_launch(ctx, "alias_decode_kernel");
     return rc;
 }

@@ -27,16 +27,20 @@ int build_word_device_tables(const uint32_t freqs[256], WordDeviceTables& t);
 
 // ---- alias coder (main_alias.cpp semantics over the rans_byte.h state machine)
 //
-// decode: divider[256] u32 + 512 x {slot_freq | sym << 24, slot_adjust}
-//   (main_alias.cpp:55-59 fused to two gathers instead of four).
+// decode: ONE 16-byte entry per bucket (main_alias.cpp:55-59 fused from four gathers to one):
+//   w0 = divider[b]
+//   w1 = slot_freqs[2b]   | sym_id[2b]   << 17        (taken when xm >= divider)
+//   w2 = slot_freqs[2b+1] | sym_id[2b+1] << 17        (taken when xm <  divider)
+//   w3 = (slot_adjust[2b] & 0xffff) | (slot_adjust[2b+1] & 0xffff) << 16
+//   xm - slot_adjust is the position inside the symbol's range, < freq <= 65536, so 16 bits of
+//   the adjust are enough: bias = (xm - adjust16) & 0xffff.
 // encode: per symbol {magic, freq, cum, shift} (same exact-division scheme) and
 //   alias_remap as u16 (values < 65536) = 128 KiB at scale_bits 16.
-struct AliasDecEntry { uint32_t freq_sym, adjust; };
+struct AliasDecEntry { uint32_t divider, alt0, alt1, adjust; };
 struct AliasEncEntry { uint32_t magic, freq, cum, shift; };
 struct AliasDeviceTables {
     uint32_t scale_bits;
-    uint32_t divider[256];
-    AliasDecEntry dec[512];
+    AliasDecEntry dec[256];
     AliasEncEntry enc[256];
     std::vector<uint16_t> remap;
 };
