@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -197,6 +198,8 @@ extern "C" int rb200_ctx_create(rb200_ctx** out, int device, void* stream)
     cudaFuncSetAttribute(word_decode_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(word_encode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(word_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmemBytes);
+    cudaFuncSetAttribute(word_encode_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(word_encode_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmemBytes);
     configure_alias_kernels();
     configure_block_kernels();
     cudaGetLastError();
@@ -379,12 +382,57 @@ int reserve_encode_workspace(rb200_ctx* ctx, uint32_t n_chunks, uint32_t slot, u
     return RB200_OK;
 }
 
+// default: three kernels (encode into per-chunk slots, tile scan, compaction).  RB200_ENCODE_PATH=fused
+// selects the single persistent launch with decoupled look-back; measured slower on B200 in round 1
+// (1.69 ms vs 1.59 ms per GiB: the look-back polling costs more than the saved pass, profiles/), kept
+// for experiments and covered by tests/test_gpu_parity.py::test_fused_encode_path.
+bool use_fused_encode()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = std::getenv("RB200_ENCODE_PATH");
+        v = (e && std::strcmp(e, "fused") == 0) ? 1 : 0;
+    }
+    return v == 1;
+}
+
+int sm_count(int device)
+{
+    static int cached_dev = -1, sms = 0;
+    if (cached_dev != device) {
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) sms = 148;
+        cached_dev = device;
+    }
+    return sms;
+}
+
+int encode_word_fused(rb200_ctx* ctx, const rb200_model* model, const uint8_t* d_in, size_t n, uint32_t chunk_syms, uint32_t n_chunks,
+                      uint8_t* d_blob, size_t blob_cap, uint64_t* d_offsets)
+{
+    const uint32_t slot = slot_bytes_for(chunk_syms);
+    const uint32_t want = (n_chunks + kEncWarps - 1) / kEncWarps;
+    uint32_t grid = static_cast<uint32_t>(sm_count(ctx->device)) * RB200_ENC_MINBLOCKS;
+    if (grid > want) grid = want;
+    int rc = reserve(ctx, ctx->scratch, static_cast<size_t>(grid) * kEncWarps * slot + 16);      // one slot per resident warp
+    if (rc == RB200_OK) rc = reserve(ctx, ctx->sizes, 16 + static_cast<size_t>(n_chunks) * sizeof(uint64_t));
+    if (rc != RB200_OK) return rc;
+    uint32_t* counter = static_cast<uint32_t*>(ctx->sizes.p);
+    uint64_t* look = reinterpret_cast<uint64_t*>(static_cast<uint8_t*>(ctx->sizes.p) + 16);
+    RB_CUDA(ctx, cudaMemsetAsync(ctx->sizes.p, 0, 16 + static_cast<size_t>(n_chunks) * sizeof(uint64_t), ctx->stream));
+    word_encode_fused_kernel<<<grid, kEncWarps * 32, kEncSmemBytes, ctx->stream>>>(
+        d_in, n, chunk_syms, n_chunks, model->d_word_enc, static_cast<uint8_t*>(ctx->scratch.p), slot, look, counter, d_blob, blob_cap,
+        d_offsets, ctx->d_status);
+    return check_launch(ctx, "word_encode_fused_kernel");
+}
+
 int encode_device(rb200_ctx* ctx, const rb200_model* model, const uint8_t* d_in, size_t n, uint32_t chunk_syms,
                   uint8_t* d_blob, size_t blob_cap, uint64_t* d_offsets)
 {
     const size_t n_chunks_sz = rb200_chunk_count(n, chunk_syms);
     if (n_chunks_sz >= (1ull << 31)) return RB200_E_ARG;
     const uint32_t n_chunks = static_cast<uint32_t>(n_chunks_sz);
+    if (n_chunks && model->coder == RB200_CODER_WORD && use_fused_encode())
+        return encode_word_fused(ctx, model, d_in, n, chunk_syms, n_chunks, d_blob, blob_cap, d_offsets);
     const uint32_t slot = slot_bytes_for(chunk_syms);
     uint8_t* scratch; uint32_t* sizes; uint64_t* tile_sums;
     int rc = reserve_encode_workspace(ctx, n_chunks, slot, &scratch, &sizes, &tile_sums);

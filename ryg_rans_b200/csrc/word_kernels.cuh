@@ -269,16 +269,15 @@ __device__ __forceinline__ void word_enc_flush(uint32_t produced, uint32_t& flus
     __syncwarp();
 }
 
-// Encode chunk `chunk` (one warp) into the END of its scratch slot.
+// Encode m symbols (one warp) as one 32-way stream that ENDS at slot_end (16-byte aligned) and grows
+// downwards; returns the stream size in bytes (warp-uniform).
 //   tab  = shared address of the 8x replicated uint4 table
 //   wsm  = shared address of this warp's 1 KiB (stage, then ring; 512-byte aligned)
-__device__ __forceinline__ void word_encode_chunk(const uint8_t* __restrict__ chunk_in, uint32_t m, uint32_t chunk,
-                                                  uint32_t tab, uint32_t wsm, uint8_t* __restrict__ scratch,
-                                                  uint32_t slot_bytes, uint32_t* __restrict__ sizes, uint32_t* __restrict__ status)
+__device__ __forceinline__ uint32_t word_encode_stream(const uint8_t* __restrict__ chunk_in, uint32_t m, uint32_t tab, uint32_t wsm,
+                                                       uint8_t* __restrict__ slot_end, uint32_t* __restrict__ status)
 {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t stage = wsm, ring = wsm + kEncStageBytes;
-    uint8_t* slot_end = scratch + static_cast<uint64_t>(chunk + 1) * slot_bytes;
     const uint32_t tab_lane = tab + (lane & (kEncReplicas - 1)) * 16;
     const uint32_t gt = lanemask_gt();
 
@@ -340,8 +339,17 @@ __device__ __forceinline__ void word_encode_chunk(const uint8_t* __restrict__ ch
         const uint32_t off = flushed + 2 * lane + 2;                 // bytes below slot_end
         *reinterpret_cast<uint16_t*>(slot_end - off) = static_cast<uint16_t>(lds_u16(ring | ((0u - off) & (kEncRingBytes - 1))));
     }
-    if (lane == 0) sizes[chunk] = produced;
     if (__any_sync(0xffffffffu, (st.flags & kWordSlots) != 0) && lane == 0) atomicOr(status, kStatSymbol);
+    return produced;
+}
+
+// chunk `chunk` into the end of its own worst-case slot of `scratch`; size to sizes[chunk]
+__device__ __forceinline__ void word_encode_chunk(const uint8_t* __restrict__ chunk_in, uint32_t m, uint32_t chunk,
+                                                  uint32_t tab, uint32_t wsm, uint8_t* __restrict__ scratch,
+                                                  uint32_t slot_bytes, uint32_t* __restrict__ sizes, uint32_t* __restrict__ status)
+{
+    const uint32_t produced = word_encode_stream(chunk_in, m, tab, wsm, scratch + static_cast<uint64_t>(chunk + 1) * slot_bytes, status);
+    if ((threadIdx.x & 31) == 0) sizes[chunk] = produced;
 }
 
 #ifndef RB200_ENC_MINBLOCKS
@@ -366,6 +374,140 @@ word_encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_sy
                       slot_bytes, sizes, status);
 }
 constexpr uint32_t kEncSmemBytes = kEncTableBytes + kEncWarps * kEncWarpSmem;
+
+// ---------------------------------------------------------------------------
+// K2f: persistent encode with the directory and the compaction fused in.
+//
+// Every warp fetches chunk ids from an atomic counter (so chunks start in order), encodes the chunk
+// into a scratch slot that belongs to the WARP (reused for each of its chunks, so the whole scratch
+// is ~resident-warps x slot and stays in L2), publishes the chunk's padded size, resolves its
+// exclusive prefix with a decoupled look-back over the chunks before it (they started earlier and
+// finish earlier, so the nearest resolved prefix is normally a few entries back), then moves its own
+// L2-hot stream to its final place in the blob and writes its directory entry.  One launch, no CTA
+// barrier in the loop, no second pass over the compressed bytes.
+// ---------------------------------------------------------------------------
+constexpr uint64_t kLookAgg = 1ull << 62, kLookPrefix = 2ull << 62, kLookValue = (1ull << 62) - 1;
+constexpr uint32_t kLookSpinLimit = 1u << 26;     // a bug must not hang the GPU: give up and flag instead
+
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t* p)
+{
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(uint64_t* p, uint64_t v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint4 ldg_l2_u128(const uint4* p)      // L2-coherent: data this kernel wrote itself
+{
+    uint4 v;
+    asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
+// exclusive prefix (sum of the padded sizes of all groups before `group`), computed by one warp
+__device__ __forceinline__ uint64_t lookback_exclusive(const uint64_t* look, uint32_t group, uint32_t lane, uint32_t* status)
+{
+    uint64_t excl = 0;
+    int64_t g = group;
+    while (g > 0) {
+        const int64_t idx = g - 1 - static_cast<int64_t>(lane);        // lane 0 looks at the nearest predecessor
+        uint64_t v;
+        uint32_t first, spins = 0;
+        for (;;) {
+            v = idx >= 0 ? ld_relaxed_u64(look + idx) : kLookPrefix;
+            const uint32_t flag = static_cast<uint32_t>(v >> 62);
+            const uint32_t pmask = __ballot_sync(0xffffffffu, flag == 2);
+            const uint32_t imask = __ballot_sync(0xffffffffu, flag == 0);
+            first = pmask ? static_cast<uint32_t>(__ffs(pmask)) - 1 : 32u;
+            const uint32_t needed = first >= 31 ? 0xffffffffu : ((2u << first) - 1);
+            if (!(imask & needed)) break;
+            if (++spins > kLookSpinLimit) {
+                if (lane == 0) atomicOr(status, kStatStream);
+                return excl;
+            }
+        }
+        uint64_t c = (lane <= first) ? (v & kLookValue) : 0;
+        for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+        excl += c;
+        if (first < 32) break;
+        g -= 32;
+    }
+    return excl;
+}
+
+// move one finished stream (it ends at src_end, 16-byte aligned) to blob[end - size .. end)
+__device__ __forceinline__ void place_stream(const uint8_t* src_end, uint32_t size, uint8_t* __restrict__ blob, uint64_t end, uint32_t lane)
+{
+    const uint32_t padded = (size + 15u) & ~15u;
+    const uint32_t gap = padded - size;
+    const uint8_t* src = src_end - size;
+    uint8_t* dst_vec0 = blob + (end - padded);
+    if (lane < 16) {
+        uint8_t v = 0;
+        if (lane >= gap) v = *reinterpret_cast<const volatile uint8_t*>(src + (lane - gap));
+        dst_vec0[lane] = v;
+    }
+    const uint4* s4 = reinterpret_cast<const uint4*>(src + (16 - gap));
+    uint4* d4 = reinterpret_cast<uint4*>(dst_vec0 + 16);
+    const uint32_t nvec = padded / 16 - 1;
+    for (uint32_t v = lane; v < nvec; v += 32) stg_stream_u128(d4 + v, ldg_l2_u128(s4 + v));
+}
+
+__global__ void __launch_bounds__(kEncWarps * 32, RB200_ENC_MINBLOCKS)
+word_encode_fused_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_syms, uint32_t n_chunks,
+                         const WordEncEntry* __restrict__ g_table, uint8_t* __restrict__ scratch, uint32_t slot_bytes,
+                         uint64_t* __restrict__ look, uint32_t* __restrict__ counter, uint8_t* __restrict__ blob, uint64_t blob_cap,
+                         uint64_t* __restrict__ offsets, uint32_t* __restrict__ status)
+{
+    extern __shared__ __align__(1024) uint8_t s_enc[];     // [32 KiB table][warps x 1 KiB]
+    uint4* s_tab = reinterpret_cast<uint4*>(s_enc);
+    for (uint32_t i = threadIdx.x; i < 256 * kEncReplicas; i += blockDim.x) s_tab[i] = word_enc_expand(g_table[i / kEncReplicas]);
+    __syncthreads();
+
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t tab = smem_addr(s_enc), wsm = tab + kEncTableBytes + warp * kEncWarpSmem;
+    uint8_t* slot_end = scratch + (static_cast<uint64_t>(blockIdx.x) * kEncWarps + warp + 1) * slot_bytes;   // this warp's own slot
+
+    // Stagger the first fetch over roughly one chunk-time.  All resident warps start together and a
+    // chunk costs the same everywhere, so without this every wave of ~7000 chunks would finish at once
+    // and each look-back would have to add up thousands of unresolved predecessors; staggered, chunks
+    // finish (and resolve) in id order and the nearest published prefix is a few hundred entries back.
+    {
+        const uint64_t slot = static_cast<uint64_t>(blockIdx.x) * kEncWarps + warp, slots = static_cast<uint64_t>(gridDim.x) * kEncWarps;
+        uint64_t ns = static_cast<uint64_t>(chunk_syms) * 8u * slot / slots;      // ~8 ns per symbol per warp when the SM is full
+        if (n_chunks < slots) ns = 0;                                             // fewer chunks than warps: nothing to order
+        if (ns > 1000000) ns = 1000000;
+        __nanosleep(static_cast<unsigned>(ns));
+    }
+    // warps are independent from here on: no CTA barrier inside the loop
+    for (;;) {
+        uint32_t chunk = 0;
+        if (lane == 0) chunk = atomicAdd(counter, 1u);     // chunks start in order, which keeps the look-back short and live
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        if (chunk >= n_chunks) break;
+        const uint64_t first = static_cast<uint64_t>(chunk) * chunk_syms;
+        const uint32_t m = static_cast<uint32_t>(min(static_cast<uint64_t>(chunk_syms), n - first));
+        const uint32_t produced = word_encode_stream(in + first, m, tab, wsm, slot_end, status);
+        const uint64_t padded = (produced + 15u) & ~15u;
+        if (lane == 0 && chunk) st_relaxed_u64(look + chunk, kLookAgg | padded);
+        const uint64_t excl = lookback_exclusive(look, chunk, lane, status);
+        const uint64_t end = excl + padded;                // E_c
+        if (lane == 0) {
+            st_relaxed_u64(look + chunk, kLookPrefix | end);
+            offsets[chunk] = end - produced;
+            if (chunk == n_chunks - 1) offsets[n_chunks] = end;
+        }
+        if (end <= blob_cap) {
+            __syncwarp();
+            place_stream(slot_end, produced, blob, end, lane);
+        } else if (lane == 0) {
+            atomicOr(status, kStatSpace);
+        }
+        __syncwarp();
+    }
+}
 
 // ---------------------------------------------------------------------------
 // K6: directory + compaction of the per-chunk slots into the final blob

@@ -180,3 +180,107 @@ def test_block_models_and_roundtrip(gpu_ctx, oracle_lib, gen, n_blocks, block_si
     assert np.array_equal(blob, oblob)
     out = gpu_ctx.blocks_decode_host(oblob, ooffs, freqs16, n_blocks, block_size, chunk)
     assert np.array_equal(out, data)
+
+
+# ---------------------------------------------------------------- alternative paths, big sizes
+
+def test_fused_encode_path(tmp_path):
+    """RB200_ENCODE_PATH=fused (persistent encode + decoupled look-back) must produce the identical container."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r)
+import oracle, ryg_rans_b200 as rb
+rng = np.random.default_rng(3)
+p = 1.0 / np.arange(1, 257) ** 1.1
+data = rng.choice(256, 3_000_017, p=p / p.sum()).astype(np.uint8)
+orc = oracle.Oracle()
+f, c = orc.model(data, 12)
+ctx = rb.Context(0)
+m = ctx.model(rb.CODER_WORD, 12, f)
+for chunk in (4096, 32, 65536):
+    blob, offs = ctx.encode_host(m, data, chunk)
+    ob, oo = orc.chunked_encode(oracle.CODER_WORD, data, f, c, chunk)
+    assert np.array_equal(offs, oo) and np.array_equal(blob, ob), chunk
+    assert np.array_equal(ctx.decode_host(m, blob, offs, data.size, chunk), data)
+print("fused ok", ctx.launches)
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RB200_ENCODE_PATH="fused")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "fused ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_host_pipeline_many_slices(gpu_ctx, oracle_lib, gen):
+    """Host-mode calls are a slice pipeline (32 MiB slices on three streams); cross several slice boundaries."""
+    n = (32 << 20) * 3 + 12345
+    data = gen("text", n, 77)
+    freqs, cum = _model(oracle_lib, data, 12)
+    model = gpu_ctx.model(WORD, 12, freqs)
+    blob, offs = gpu_ctx.encode_host(model, data, 8192)
+    assert blob.size % 16 == 0 and offs[-1] == blob.size
+    # slices are independent containers that were concatenated: check a chunk on each side of a slice boundary
+    for c in (0, 4095, 4096, 8191, 8192, len(offs) - 2):
+        lo = c * 8192
+        s = oracle_lib.encode(orc.CODER_WORD, data[lo:lo + 8192], freqs, cum, 32)
+        end = int(offs[c + 1]) & ~15
+        assert np.array_equal(blob[int(offs[c]):end], s), c
+    out = gpu_ctx.decode_host(model, blob, offs, n, 8192)
+    assert np.array_equal(out, data)
+    model.close()
+
+
+@pytest.mark.parametrize("coder,sb,kind", [(WORD, 12, "uniform"), (ALIAS, 16, "zipf")])
+def test_full_size_roundtrip_properties(gpu_ctx, coder, sb, kind):
+    """BASELINE sizes (1 GiB per GPU), checked through size-independent properties: device round trip is the
+    identity, the directory is monotone and 16-byte end-aligned, the blob size equals the directory's last
+    entry, and decoding after corrupting one stream is reported."""
+    import torch
+    import ryg_rans_b200 as rb
+    n, chunk = 1 << 30, 8192
+    g = torch.Generator(device="cuda")
+    g.manual_seed(1234)
+    if kind == "uniform":
+        data = torch.randint(0, 256, (n,), dtype=torch.uint8, device="cuda", generator=g)
+    else:
+        p = 1.0 / torch.arange(1, 257, dtype=torch.float64) ** 1.1
+        cdf = torch.cumsum(p / p.sum(), 0).to(device="cuda", dtype=torch.float32)
+        data = torch.empty(n, dtype=torch.uint8, device="cuda")
+        for lo in range(0, n, 1 << 26):
+            u = torch.rand(1 << 26, device="cuda", generator=g)
+            data[lo:lo + (1 << 26)] = torch.searchsorted(cdf, u).clamp_(max=255).to(torch.uint8)
+    counts = gpu_ctx.histogram_device(data.data_ptr(), n)
+    assert int(counts.sum()) == n
+    assert np.array_equal(counts, torch.bincount(data.view(torch.uint8).to(torch.int64), minlength=256).cpu().numpy().astype(np.uint64))
+    st = rb.SymbolStats()
+    st.freqs[:] = counts.astype(np.uint32)
+    st.normalize_freqs(1 << sb)
+    model = gpu_ctx.model(coder, sb, st.freqs)
+    n_chunks = gpu_ctx.chunk_count(n, chunk)
+    cap = gpu_ctx.encode_bound(n, chunk)
+    blob = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    offsets = torch.zeros(n_chunks + 1, dtype=torch.int64, device="cuda")
+    out = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    gpu_ctx.encode_device(model, data.data_ptr(), n, chunk, blob.data_ptr(), cap, offsets.data_ptr())
+    gpu_ctx.sync()
+    size = int(offsets[-1])
+    assert size % 16 == 0 and 0 < size <= cap
+    d = offsets[1:] - offsets[:-1]
+    assert bool((d > 0).all())                                   # monotone
+    ends = offsets[1:] & ~15
+    sizes = ends - offsets[:-1]
+    assert int(sizes.min()) >= 128 and int((ends[1:] - ends[:-1] - ((sizes[1:] + 15) & ~15)).abs().max()) == 0
+    gpu_ctx.decode_device(model, blob.data_ptr(), size, offsets.data_ptr(), chunk, out.data_ptr(), n)
+    gpu_ctx.sync()
+    assert torch.equal(out, data)
+    # corrupt one stream in the middle of the blob
+    mid = int(offsets[n_chunks // 2]) + 200
+    blob[mid:mid + 64] ^= 0x3C
+    gpu_ctx.decode_device(model, blob.data_ptr(), size, offsets.data_ptr(), chunk, out.data_ptr(), n)
+    with pytest.raises(rb.RansError) as ei:
+        gpu_ctx.sync()
+    assert ei.value.code == -4
+    model.close()
+    del data, blob, out, offsets
+    torch.cuda.empty_cache()
