@@ -47,8 +47,10 @@ extern "C" {
 #define RB200_MEM_DEVICE  1   /* device pointers; the call only enqueues on the stream     */
 
 /* coder families (one per reference header / driver) */
-#define RB200_CODER_WORD    0 /* rans_word_sse41.h: 32-bit state, u16 renorm, scale_bits = 12 */
-#define RB200_CODER_ALIAS   2 /* rans_byte.h state machine + main_alias.cpp alias tables      */
+#define RB200_CODER_WORD    0 /* rans_word_sse41.h: 32-bit state, u16 renorm, scale_bits = 12          */
+#define RB200_CODER_BYTE    1 /* rans_byte.h + cum2sym lookup as in main.cpp, scale_bits 8..16           */
+#define RB200_CODER_ALIAS   2 /* rans_byte.h state machine + main_alias.cpp alias tables, scale_bits 8..16 */
+#define RB200_CODER_RANS64  3 /* rans64.h: 64-bit state, u32 renorm, cum2sym lookup as in main64.cpp      */
 
 #define RB200_LANES 32        /* interleave width of one chunk stream = one warp */
 
@@ -95,9 +97,10 @@ uint64_t rb200_launch_count(const rb200_ctx* ctx);
 /* ---------------------------------------------------------------- device model */
 
 /* Upload the coding tables for one model.  freqs must already be normalised to
- * 1 << scale_bits (WORD: scale_bits must be 12, rans_word_sse41.h:37; ALIAS: 8..16,
- * main_alias.cpp:276 uses 16).  Replaces the table set-up at main_simd.cpp:141-143 /
- * main_alias.cpp:279-282. */
+ * 1 << scale_bits (WORD: scale_bits must be 12, rans_word_sse41.h:37; BYTE / ALIAS / RANS64:
+ * 8..16 -- main.cpp:136 and main64.cpp:136 use 14, main_alias.cpp:276 uses 16; BYTE needs every
+ * freq < 65536 like the reference's 16-bit RansDecSymbol).  Replaces the table set-up at
+ * main.cpp:145-162 / main64.cpp:145-164 / main_simd.cpp:141-143 / main_alias.cpp:279-282. */
 int rb200_model_create(rb200_ctx* ctx, int coder, uint32_t scale_bits,
                        const uint32_t freqs[256], rb200_model** out);
 void rb200_model_destroy(rb200_model* m);

@@ -638,7 +638,7 @@ long orc_chunked_encode(int coder, const uint8_t *in, size_t n,
     if (chunk_syms == 0 || align == 0)
         return ORC_E_ARG;
     size_t n_chunks = (n + chunk_syms - 1) / chunk_syms;
-    size_t tmp_cap = 2 * chunk_syms + 8 * (size_t)nlanes + 64;
+    size_t tmp_cap = 2 * chunk_syms + 16 * (size_t)nlanes + 256;
     uint8_t *tmp = (uint8_t *)malloc(tmp_cap);
     if (!tmp) return ORC_E_SPACE;
     size_t end_prev = 0;

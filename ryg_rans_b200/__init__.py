@@ -9,9 +9,9 @@ library is missing or no GPU is visible, calls fail loudly.
 from .build import build, LIB_PATH  # noqa: F401
 from .api import (  # noqa: F401
     Lib, Context, Model, RansError, SymbolStats,
-    CODER_WORD, CODER_ALIAS, MEM_HOST, MEM_DEVICE, LANES,
+    CODER_WORD, CODER_BYTE, CODER_ALIAS, CODER_RANS64, MEM_HOST, MEM_DEVICE, LANES,
     load,
 )
 
 __all__ = ["build", "load", "Lib", "Context", "Model", "RansError", "SymbolStats",
-           "CODER_WORD", "CODER_ALIAS", "MEM_HOST", "MEM_DEVICE", "LANES", "LIB_PATH"]
+           "CODER_WORD", "CODER_BYTE", "CODER_ALIAS", "CODER_RANS64", "MEM_HOST", "MEM_DEVICE", "LANES", "LIB_PATH"]

@@ -6,7 +6,7 @@ import numpy as np
 
 from .build import LIB_PATH, build
 
-CODER_WORD, CODER_ALIAS = 0, 2
+CODER_WORD, CODER_BYTE, CODER_ALIAS, CODER_RANS64 = 0, 1, 2, 3
 MEM_HOST, MEM_DEVICE = 0, 1
 LANES = 32
 

@@ -21,21 +21,34 @@ constexpr uint32_t kByteL = 1u << 23;   // RANS_BYTE_L, rans_byte.h:50
 constexpr int kAliasDecWarps = 16;
 constexpr uint32_t kAliasDecReplicas = 8;    // quarter-warp lanes hit 8 different 16-byte bank groups
 
-// RansDecGetAlias (main_alias.cpp:252-267) + RansDecRenorm (rans_byte.h:307-318), warp-wide.
-// tab_lane = shared address of this lane's replica of the 256 x 16 B bucket table.
+// One decode step of the byte-renormalising coders for the whole warp.
+//   ALIAS:  RansDecGetAlias (main_alias.cpp:252-267); tab_lane = this lane's replica of the 256 x 16 B
+//           bucket table.
+//   !ALIAS: RansDecGet -> cum2sym -> RansDecAdvanceSymbolStep (rans_byte.h:125-128, main.cpp:200,
+//           rans_byte.h:291-304); tab_lane = shared address of cum2sym[1 << sb], followed by the
+//           256 x {start | freq << 16} table.
+// then RansDecRenorm (rans_byte.h:307-318) for both.
+template <bool ALIAS>
 __device__ __forceinline__ void alias_dec_step(uint32_t& x, uint32_t& cursor, uint32_t tab_lane, uint32_t ring, uint8_t* o,
                                                uint32_t lt, uint32_t sb, bool active)
 {
     bool n1 = false, n2 = false;
     if (active) {
-        const uint32_t xm = x & ((1u << sb) - 1);                          // :258
-        const uint32_t bucket = xm >> (sb - 8);                            // :259
-        const uint4 e = lds_u128_ro(tab_lane + bucket * (kAliasDecReplicas * 16));
-        const bool own = xm < e.x;                                         // :261 (bucket2 = 2 * bucket + 1)
-        const uint32_t fs = own ? e.z : e.y;                               // slot_freqs | sym_id << 17
-        const uint32_t adj = own ? (e.w >> 16) : (e.w & 0xffffu);
-        x = (fs & 0x1ffffu) * (x >> sb) + ((xm - adj) & 0xffffu);          // :265
-        *o = static_cast<uint8_t>(fs >> 17);                               // :266
+        const uint32_t xm = x & ((1u << sb) - 1);                          // main_alias.cpp:258 / rans_byte.h:127
+        if (ALIAS) {
+            const uint32_t bucket = xm >> (sb - 8);                        // :259
+            const uint4 e = lds_u128_ro(tab_lane + bucket * (kAliasDecReplicas * 16));
+            const bool own = xm < e.x;                                     // :261 (bucket2 = 2 * bucket + 1)
+            const uint32_t fs = own ? e.z : e.y;                           // slot_freqs | sym_id << 17
+            const uint32_t adj = own ? (e.w >> 16) : (e.w & 0xffffu);
+            x = (fs & 0x1ffffu) * (x >> sb) + ((xm - adj) & 0xffffu);      // :265
+            *o = static_cast<uint8_t>(fs >> 17);                           // :266
+        } else {
+            const uint32_t s = lds_u8_ro(tab_lane + xm);                   // cum2sym, main.cpp:200
+            const uint32_t ds = lds_u32_ro(tab_lane + (1u << sb) + 4u * s);   // RansDecSymbol {start, freq}
+            x = (ds >> 16) * (x >> sb) + xm - (ds & 0xffffu);              // rans_byte.h:297
+            *o = static_cast<uint8_t>(s);
+        }
         n1 = x < kByteL;
         n2 = x < (kByteL >> 8);
     }
@@ -53,16 +66,24 @@ __device__ __forceinline__ void alias_dec_step(uint32_t& x, uint32_t& cursor, ui
     }
 }
 
+// ALIAS: g_tab = 256 x AliasDecEntry.  !ALIAS: g_tab = cum2sym[1 << sb] followed by 256 x u32 {start | freq << 16}.
+template <bool ALIAS>
 __global__ void __launch_bounds__(kAliasDecWarps * 32, 4)
 alias_decode_kernel(const uint8_t* __restrict__ blob, uint64_t blob_size, const uint64_t* __restrict__ offsets, uint32_t sb,
-                    const AliasDecEntry* __restrict__ g_dec, uint8_t* __restrict__ out, uint64_t n, uint32_t chunk_syms,
+                    const void* __restrict__ g_tab, uint8_t* __restrict__ out, uint64_t n, uint32_t chunk_syms,
                     uint32_t n_chunks, uint32_t* __restrict__ status)
 {
-    extern __shared__ __align__(1024) uint8_t s_adec[];       // [16 x 1 KiB rings][32 KiB table]
+    extern __shared__ __align__(1024) uint8_t s_adec[];       // [16 x 1 KiB rings][table]
     uint4* s_tab = reinterpret_cast<uint4*>(s_adec + kAliasDecWarps * kRingBytes);
-    for (uint32_t i = threadIdx.x; i < 256 * kAliasDecReplicas; i += blockDim.x) {
-        const AliasDecEntry e = g_dec[i / kAliasDecReplicas];
-        s_tab[i] = make_uint4(e.divider, e.alt0, e.alt1, e.adjust);
+    if (ALIAS) {
+        const AliasDecEntry* g_dec = static_cast<const AliasDecEntry*>(g_tab);
+        for (uint32_t i = threadIdx.x; i < 256 * kAliasDecReplicas; i += blockDim.x) {
+            const AliasDecEntry e = g_dec[i / kAliasDecReplicas];
+            s_tab[i] = make_uint4(e.divider, e.alt0, e.alt1, e.adjust);
+        }
+    } else {
+        const uint32_t vecs = ((1u << sb) + 1024) / 16;
+        for (uint32_t i = threadIdx.x; i < vecs; i += blockDim.x) s_tab[i] = static_cast<const uint4*>(g_tab)[i];
     }
     __syncthreads();
 
@@ -89,24 +110,24 @@ alias_decode_kernel(const uint8_t* __restrict__ blob, uint64_t blob_size, const 
     cursor += kHeaderBytes;
 
     const uint32_t lt = lanemask_lt();
-    const uint32_t tab_lane = smem_addr(s_tab) + (lane & (kAliasDecReplicas - 1)) * 16;
+    const uint32_t tab_lane = smem_addr(s_tab) + (ALIAS ? (lane & (kAliasDecReplicas - 1)) * 16 : 0);
     uint8_t* o = out + first + lane;
     const uint32_t steps = m >> 5, rem = m & 31;
     uint32_t g = 0;
     for (; g + 4 <= steps; g += 4) {
         win.top_up(cursor, lane);
-        alias_dec_step(x, cursor, tab_lane, win.ring, o, lt, sb, true);
-        alias_dec_step(x, cursor, tab_lane, win.ring, o + 32, lt, sb, true);
-        alias_dec_step(x, cursor, tab_lane, win.ring, o + 64, lt, sb, true);
-        alias_dec_step(x, cursor, tab_lane, win.ring, o + 96, lt, sb, true);
+        alias_dec_step<ALIAS>(x, cursor, tab_lane, win.ring, o, lt, sb, true);
+        alias_dec_step<ALIAS>(x, cursor, tab_lane, win.ring, o + 32, lt, sb, true);
+        alias_dec_step<ALIAS>(x, cursor, tab_lane, win.ring, o + 64, lt, sb, true);
+        alias_dec_step<ALIAS>(x, cursor, tab_lane, win.ring, o + 96, lt, sb, true);
         o += 128;
     }
     win.top_up(cursor, lane);
     for (; g < steps; g++) {
-        alias_dec_step(x, cursor, tab_lane, win.ring, o, lt, sb, true);
+        alias_dec_step<ALIAS>(x, cursor, tab_lane, win.ring, o, lt, sb, true);
         o += 32;
     }
-    if (rem) alias_dec_step(x, cursor, tab_lane, win.ring, o, lt, sb, lane < rem);
+    if (rem) alias_dec_step<ALIAS>(x, cursor, tab_lane, win.ring, o, lt, sb, lane < rem);
 
     const bool bad = (cursor != static_cast<uint32_t>(end)) || (x != kByteL);
     if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(status, kStatStream);
@@ -139,16 +160,21 @@ struct AliasEncState {
     uint32_t flags;
 };
 
+// One encode step of the byte-renormalising coders for the whole warp.
+//   ALIAS:  RansEncPutAlias (main_alias.cpp:241-250); table {magic, freq, cum, shift}
+//   !ALIAS: RansEncPutSymbol (rans_byte.h:258-280);   table {x_max, rcp_freq, bias, cmpl_freq | rcp_shift << 16}
+//           = RansEncSymbol (rans_byte.h:159-165), bit 31 of the last word marks a symbol outside the model
+template <bool ALIAS>
 __device__ __forceinline__ void alias_enc_step(AliasEncState& st, uint32_t sym, uint32_t tab_lane, uint32_t remap, uint32_t ring,
                                                uint32_t gt, uint32_t sb, bool active)
 {
     bool n1 = false, n2 = false;
     uint4 e = make_uint4(0, 1, 0, 0);
     if (active) {
-        e = lds_u128_ro(tab_lane + sym * (kEncReplicas * 16));   // {magic, freq, cum, shift}
+        e = lds_u128_ro(tab_lane + sym * (kEncReplicas * 16));
         st.flags |= e.w;
-        const uint32_t x_max = e.y << (31 - sb);                  // ((L >> sb) << 8) * freq, rans_byte.h:64
-        n1 = st.x >= x_max;                                       // :65
+        const uint32_t x_max = ALIAS ? e.y << (31 - sb) : e.x;   // ((L >> sb) << 8) * freq, rans_byte.h:64 / :197
+        n1 = st.x >= x_max;                                       // :65 / :265
         n2 = (st.x >> 8) >= x_max;                                // second trip of the do/while, :67-70
     }
     const uint32_t m1 = __ballot_sync(0xffffffffu, n1);
@@ -162,14 +188,20 @@ __device__ __forceinline__ void alias_enc_step(AliasEncState& st, uint32_t sym, 
     }
     st.wpos -= __popc(m1) + __popc(m2);
     if (active) {
-        const uint32_t hi = __umulhi(st.x, e.x);                                   // exact x / freq, as in the word encoder
-        const uint32_t lo = st.x + hi;
-        const uint32_t q = funnel_shr_wrap(lo, lo < hi ? 1u : 0u, e.w);
-        const uint32_t r = st.x - q * e.y;                                         // x % freq
-        st.x = (q << sb) + lds_u16_ro(remap + 2u * (r + e.z));                     // main_alias.cpp:249
+        if (ALIAS) {
+            const uint32_t hi = __umulhi(st.x, e.x);                               // exact x / freq, as in the word encoder
+            const uint32_t lo = st.x + hi;
+            const uint32_t q = funnel_shr_wrap(lo, lo < hi ? 1u : 0u, e.w);
+            const uint32_t r = st.x - q * e.y;                                     // x % freq
+            st.x = (q << sb) + lds_u16_ro(remap + 2u * (r + e.z));                 // main_alias.cpp:249
+        } else {
+            const uint32_t q = __umulhi(st.x, e.y) >> ((e.w >> 16) & 31u);         // rans_byte.h:278
+            st.x = st.x + e.z + q * (e.w & 0xffffu);                               // :279
+        }
     }
 }
 
+template <bool ALIAS>
 __device__ __forceinline__ void alias_encode_chunk(const uint8_t* __restrict__ chunk_in, uint32_t m, uint32_t chunk, uint32_t tab,
                                                    uint32_t remap, uint32_t wsm, uint32_t sb, uint8_t* __restrict__ scratch,
                                                    uint32_t slot_bytes, uint32_t* __restrict__ sizes, uint32_t* __restrict__ status)
@@ -194,11 +226,11 @@ __device__ __forceinline__ void alias_encode_chunk(const uint8_t* __restrict__ c
     if (rem) {
         const bool active = lane < rem;
         const uint32_t s = active ? chunk_in[static_cast<uint64_t>(steps) * 32 + lane] : 0;
-        alias_enc_step(st, s, tab_lane, remap, ring, gt, sb, active);
+        alias_enc_step<ALIAS>(st, s, tab_lane, remap, ring, gt, sb, active);
     }
     for (uint32_t g = steps; g > nblk * 16; g--) {
         const uint32_t s = chunk_in[static_cast<uint64_t>(g - 1) * 32 + lane];
-        alias_enc_step(st, s, tab_lane, remap, ring, gt, sb, true);
+        alias_enc_step<ALIAS>(st, s, tab_lane, remap, ring, gt, sb, true);
         if (((g - 1) & 3) == 0) word_enc_flush(kEncRingBytes - 1 - st.wpos, flushed, ring, slot_end, lane);
     }
     word_enc_flush(kEncRingBytes - 1 - st.wpos, flushed, ring, slot_end, lane);
@@ -218,7 +250,7 @@ __device__ __forceinline__ void alias_encode_chunk(const uint8_t* __restrict__ c
         for (int grp = 3; grp >= 0; grp--) {
 #pragma unroll
             for (int j = 3; j >= 0; j--)
-                alias_enc_step(st, lds_u8(stage + (grp * 4 + j) * 32 + lane), tab_lane, remap, ring, gt, sb, true);
+                alias_enc_step<ALIAS>(st, lds_u8(stage + (grp * 4 + j) * 32 + lane), tab_lane, remap, ring, gt, sb, true);
             if (kEncRingBytes - 1 - st.wpos - flushed >= 256) word_enc_flush(kEncRingBytes - 1 - st.wpos, flushed, ring, slot_end, lane);
         }
     }
@@ -241,6 +273,8 @@ __device__ __forceinline__ void alias_encode_chunk(const uint8_t* __restrict__ c
     if (__any_sync(0xffffffffu, (st.flags & kEncBadSymbol) != 0) && lane == 0) atomicOr(status, kStatSymbol);
 }
 
+// !ALIAS: g_enc holds RansEncSymbol images {x_max, rcp_freq, bias, cmpl | shift << 16}, g_remap is unused
+template <bool ALIAS>
 __global__ void __launch_bounds__(kAliasEncWarps * 32, 1)
 alias_encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_syms, uint32_t n_chunks, uint32_t sb,
                     const AliasEncEntry* __restrict__ g_enc, const uint16_t* __restrict__ g_remap,
@@ -253,9 +287,10 @@ alias_encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_s
     for (uint32_t i = threadIdx.x; i < 256 * kEncReplicas; i += blockDim.x) {
         const AliasEncEntry e = g_enc[i / kEncReplicas];
         // a symbol the model does not contain: keep the step well defined (freq 1), flag it
-        s_tab[i] = (e.shift & kEncBadSymbol) ? make_uint4(0, 1, 0, kEncBadSymbol) : make_uint4(e.magic, e.freq, e.cum, e.shift);
+        if (ALIAS) s_tab[i] = (e.shift & kEncBadSymbol) ? make_uint4(0, 1, 0, kEncBadSymbol) : make_uint4(e.magic, e.freq, e.cum, e.shift);
+        else       s_tab[i] = make_uint4(e.magic, e.freq, e.cum, e.shift);          // the host already made bad entries safe
     }
-    const uint32_t remap_vecs = (2u << sb) / 16;
+    const uint32_t remap_vecs = ALIAS ? (2u << sb) / 16 : 0;
     for (uint32_t i = threadIdx.x; i < remap_vecs; i += blockDim.x) s_remap[i] = reinterpret_cast<const uint4*>(g_remap)[i];
     __syncthreads();
 
@@ -264,7 +299,7 @@ alias_encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_s
     for (uint32_t chunk = blockIdx.x * kAliasEncWarps + warp; chunk < n_chunks; chunk += gridDim.x * kAliasEncWarps) {
         const uint64_t first = static_cast<uint64_t>(chunk) * chunk_syms;
         const uint32_t m = static_cast<uint32_t>(min(static_cast<uint64_t>(chunk_syms), n - first));
-        alias_encode_chunk(in + first, m, chunk, base + kAliasEncWarps * kEncWarpSmem, base + kAliasEncFixedSmem,
+        alias_encode_chunk<ALIAS>(in + first, m, chunk, base + kAliasEncWarps * kEncWarpSmem, base + kAliasEncFixedSmem,
                            base + warp * kEncWarpSmem, sb, scratch, slot_bytes, sizes, status);
     }
 }
@@ -282,10 +317,14 @@ inline int alias_sm_count()
 
 inline void configure_alias_kernels()
 {
-    cudaFuncSetAttribute(alias_decode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(alias_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAliasDecSmem);
-    cudaFuncSetAttribute(alias_encode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(alias_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAliasEncFixedSmem + (2u << 16));
+    cudaFuncSetAttribute(alias_decode_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(alias_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAliasDecSmem);
+    cudaFuncSetAttribute(alias_decode_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(alias_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAliasDecWarps * kRingBytes + 1024 + (1u << 16));
+    cudaFuncSetAttribute(alias_encode_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(alias_encode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAliasEncFixedSmem + (2u << 16));
+    cudaFuncSetAttribute(alias_encode_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(alias_encode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAliasEncFixedSmem);
 }
 
 inline int launch_alias_encode(cudaStream_t stream, const uint8_t* d_in, uint64_t n, uint32_t chunk_syms, uint32_t n_chunks,
@@ -295,8 +334,12 @@ inline int launch_alias_encode(cudaStream_t stream, const uint8_t* d_in, uint64_
     uint32_t grid = (n_chunks + kAliasEncWarps - 1) / kAliasEncWarps;
     const uint32_t sms = static_cast<uint32_t>(alias_sm_count());
     if (grid > sms) grid = sms;                       // persistent: one CTA per SM, chunks strided over CTAs
-    alias_encode_kernel<<<grid, kAliasEncWarps * 32, kAliasEncFixedSmem + (2u << sb), stream>>>(d_in, n, chunk_syms, n_chunks, sb, enc,
-                                                                                                 remap, scratch, slot, sizes, status);
+    if (remap)
+        alias_encode_kernel<true><<<grid, kAliasEncWarps * 32, kAliasEncFixedSmem + (2u << sb), stream>>>(
+            d_in, n, chunk_syms, n_chunks, sb, enc, remap, scratch, slot, sizes, status);
+    else      // rans_byte cum2sym coder: same kernel without the alias remap
+        alias_encode_kernel<false><<<grid, kAliasEncWarps * 32, kAliasEncFixedSmem, stream>>>(
+            d_in, n, chunk_syms, n_chunks, sb, enc, nullptr, scratch, slot, sizes, status);
     return 0;
 }
 
@@ -305,8 +348,18 @@ inline int launch_alias_decode(cudaStream_t stream, const uint8_t* blob, uint64_
                                uint32_t* status)
 {
     const uint32_t grid = (n_chunks + kAliasDecWarps - 1) / kAliasDecWarps;
-    alias_decode_kernel<<<grid, kAliasDecWarps * 32, kAliasDecSmem, stream>>>(blob, blob_size, offsets, sb, dec, out, n, chunk_syms,
-                                                                              n_chunks, status);
+    alias_decode_kernel<true><<<grid, kAliasDecWarps * 32, kAliasDecSmem, stream>>>(blob, blob_size, offsets, sb, dec, out, n, chunk_syms,
+                                                                                    n_chunks, status);
+    return 0;
+}
+
+// rans_byte cum2sym decode: table = cum2sym[1 << sb] followed by 256 x u32 {start | freq << 16}
+inline int launch_byte_decode(cudaStream_t stream, const uint8_t* blob, uint64_t blob_size, const uint64_t* offsets, uint32_t sb,
+                              const uint8_t* table, uint8_t* out, uint64_t n, uint32_t chunk_syms, uint32_t n_chunks, uint32_t* status)
+{
+    const uint32_t grid = (n_chunks + kAliasDecWarps - 1) / kAliasDecWarps;
+    alias_decode_kernel<false><<<grid, kAliasDecWarps * 32, kAliasDecWarps * kRingBytes + 1024 + (1u << sb), stream>>>(
+        blob, blob_size, offsets, sb, table, out, n, chunk_syms, n_chunks, status);
     return 0;
 }
 

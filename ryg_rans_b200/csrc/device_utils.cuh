@@ -55,6 +55,12 @@ __device__ __forceinline__ uint32_t lds_u32_ro(uint32_t addr)
     asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ uint32_t lds_u8_ro(uint32_t addr)
+{
+    uint32_t v;
+    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ uint2 lds_u64_ro(uint32_t addr)
 {
     uint2 v;

@@ -224,4 +224,76 @@ int build_alias_device_tables(const uint32_t freqs[256], uint32_t scale_bits, Al
     return RB200_OK;
 }
 
+int build_byte_device_tables(const uint32_t freqs[256], uint32_t scale_bits, ByteDeviceTables& t)
+{
+    if (scale_bits < 8 || scale_bits > 16) return RB200_E_ARG;
+    const uint32_t M = 1u << scale_bits;
+    uint32_t cum[257];
+    cum[0] = 0;
+    for (int s = 0; s < 256; s++) {
+        if (freqs[s] >= 65536u || freqs[s] > M) return RB200_E_MODEL;   // RansDecSymbol.freq is 16 bits wide
+        cum[s + 1] = cum[s] + freqs[s];
+    }
+    if (cum[256] != M) return RB200_E_MODEL;
+    t.scale_bits = scale_bits;
+    t.dec.assign(M + 1024, 0);
+    uint32_t* dsyms = reinterpret_cast<uint32_t*>(t.dec.data() + M);
+    for (int s = 0; s < 256; s++) {
+        std::memset(t.dec.data() + cum[s], s, freqs[s]);                // cum2sym, main.cpp:145-148
+        dsyms[s] = cum[s] | (freqs[s] << 16);                           // RansDecSymbolInit, rans_byte.h:246-252
+        const uint32_t f = freqs[s];
+        const uint32_t x_max = ((1u << 23 >> scale_bits) << 8) * (f ? f : 1);    // rans_byte.h:197
+        if (f == 0) {           // never valid to encode (rans_byte.h:260): act like freq 1, flag it
+            t.enc[s] = {x_max, 0xffffffffu, M - 1, ((M - 1) & 0xffffu) | kEncBadSymbol};
+        } else if (f == 1) {    // rans_byte.h:199-228
+            t.enc[s] = {x_max, 0xffffffffu, cum[s] + M - 1, (M - 1) & 0xffffu};
+        } else {                // rans_byte.h:229-242
+            const uint32_t sh = ceil_log2(f);
+            const uint32_t rcp = static_cast<uint32_t>(((1ull << (sh + 31)) + f - 1) / f);
+            t.enc[s] = {x_max, rcp, cum[s], ((M - f) & 0xffffu) | ((sh - 1) << 16)};
+        }
+    }
+    return RB200_OK;
+}
+
+int build_rans64_device_tables(const uint32_t freqs[256], uint32_t scale_bits, Rans64DeviceTables& t)
+{
+    if (scale_bits < 8 || scale_bits > 16) return RB200_E_ARG;
+    const uint32_t M = 1u << scale_bits;
+    uint32_t cum[257];
+    cum[0] = 0;
+    for (int s = 0; s < 256; s++) {
+        if (freqs[s] > M) return RB200_E_MODEL;
+        cum[s + 1] = cum[s] + freqs[s];
+    }
+    if (cum[256] != M) return RB200_E_MODEL;
+    t.scale_bits = scale_bits;
+    t.dec.assign(M + 2048, 0);
+    uint32_t* dsyms = reinterpret_cast<uint32_t*>(t.dec.data() + M);
+    for (int s = 0; s < 256; s++) {
+        std::memset(t.dec.data() + cum[s], s, freqs[s]);                // cum2sym, main64.cpp:145-148
+        dsyms[2 * s] = cum[s];                                          // Rans64DecSymbolInit, rans64.h:250-256
+        dsyms[2 * s + 1] = freqs[s];
+        const uint32_t f = freqs[s];
+        uint64_t rcp;
+        uint32_t shift, bias, flag = 0;
+        if (f < 2) {                                                    // rans64.h:199-228 (freq 0: same, flagged)
+            rcp = ~0ull;
+            shift = 0;
+            bias = (f ? cum[s] : 0) + M - 1;
+            if (f == 0) flag = kEncBadSymbol;
+        } else {                                                        // rans64.h:229-246
+            const uint32_t k = ceil_log2(f);
+            const unsigned __int128 one = 1;
+            rcp = static_cast<uint64_t>(((one << (k + 63)) + f - 1) / f);
+            shift = k - 1;
+            bias = cum[s];
+        }
+        const uint32_t fe = f ? f : 1;
+        const uint32_t e[8] = {static_cast<uint32_t>(rcp), static_cast<uint32_t>(rcp >> 32), fe, bias, M - fe, shift | flag, 0, 0};
+        std::memcpy(t.enc[s], e, sizeof e);
+    }
+    return RB200_OK;
+}
+
 }  // namespace rb200

@@ -17,6 +17,7 @@
 
 #include "alias_kernels.cuh"
 #include "block_kernels.cuh"
+#include "rans64_kernels.cuh"
 #include "tables.h"
 #include "word_kernels.cuh"
 
@@ -60,6 +61,10 @@ struct rb200_model {
     AliasDecEntry* d_alias_dec = nullptr;    // 256 x 16 B
     AliasEncEntry* d_alias_enc = nullptr;    // 256
     uint16_t* d_alias_remap = nullptr;       // 1 << scale_bits
+    uint8_t* d_byte_dec = nullptr;           // cum2sym[1 << scale_bits] + 256 x u32
+    AliasEncEntry* d_byte_enc = nullptr;     // 256 RansEncSymbol images
+    uint8_t* d_r64_dec = nullptr;            // cum2sym[1 << scale_bits] + 256 x {start, freq}
+    uint4* d_r64_enc = nullptr;              // 256 x 32 B Rans64EncSymbol images
 };
 
 namespace {
@@ -104,7 +109,8 @@ void release(DevBuf& b)
 }
 
 inline size_t round16(size_t v) { return (v + 15) & ~static_cast<size_t>(15); }
-inline uint32_t slot_bytes_for(uint32_t chunk_syms) { return static_cast<uint32_t>(round16(kHeaderBytes + 2ull * chunk_syms)); }
+constexpr size_t kBoundFixed = 512;   // headers (128 B; 256 B for rans64) + one extra unit per lane
+inline uint32_t slot_bytes_for(uint32_t chunk_syms) { return static_cast<uint32_t>(round16(kBoundFixed + 2ull * chunk_syms)); }
 
 int status_to_code(uint32_t bits)
 {
@@ -202,6 +208,7 @@ extern "C" int rb200_ctx_create(rb200_ctx** out, int device, void* stream)
     cudaFuncSetAttribute(word_encode_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmemBytes);
     configure_alias_kernels();
     configure_block_kernels();
+    configure_rans64_kernels();
     cudaGetLastError();
     *out = ctx;
     return RB200_OK;
@@ -259,6 +266,8 @@ extern "C" void rb200_model_destroy(rb200_model* m)
     cudaStreamSynchronize(m->ctx->stream);
     cudaFree(m->d_word_dec); cudaFree(m->d_word_enc);
     cudaFree(m->d_alias_dec); cudaFree(m->d_alias_enc); cudaFree(m->d_alias_remap);
+    cudaFree(m->d_byte_dec); cudaFree(m->d_byte_enc);
+    cudaFree(m->d_r64_dec); cudaFree(m->d_r64_enc);
     delete m;
 }
 
@@ -301,6 +310,28 @@ extern "C" int rb200_model_create(rb200_ctx* ctx, int coder, uint32_t scale_bits
             if (e == cudaSuccess) e = cudaMemcpy(m->d_alias_remap, t->remap.data(), remap_bytes, cudaMemcpyHostToDevice);
         }
         delete t;
+    } else if (coder == RB200_CODER_BYTE) {
+        ByteDeviceTables* t = new (std::nothrow) ByteDeviceTables;
+        if (!t) { delete m; return RB200_E_NOMEM; }
+        rc = build_byte_device_tables(freqs, scale_bits, *t);
+        if (rc == RB200_OK) {
+            e = cudaMalloc(&m->d_byte_dec, t->dec.size());
+            if (e == cudaSuccess) e = cudaMalloc(&m->d_byte_enc, sizeof t->enc);
+            if (e == cudaSuccess) e = cudaMemcpy(m->d_byte_dec, t->dec.data(), t->dec.size(), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(m->d_byte_enc, t->enc, sizeof t->enc, cudaMemcpyHostToDevice);
+        }
+        delete t;
+    } else if (coder == RB200_CODER_RANS64) {
+        Rans64DeviceTables* t = new (std::nothrow) Rans64DeviceTables;
+        if (!t) { delete m; return RB200_E_NOMEM; }
+        rc = build_rans64_device_tables(freqs, scale_bits, *t);
+        if (rc == RB200_OK) {
+            e = cudaMalloc(&m->d_r64_dec, t->dec.size());
+            if (e == cudaSuccess) e = cudaMalloc(&m->d_r64_enc, sizeof t->enc);
+            if (e == cudaSuccess) e = cudaMemcpy(m->d_r64_dec, t->dec.data(), t->dec.size(), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(m->d_r64_enc, t->enc, sizeof t->enc, cudaMemcpyHostToDevice);
+        }
+        delete t;
     } else {
         delete m;
         return RB200_E_ARG;
@@ -324,16 +355,17 @@ extern "C" size_t rb200_chunk_count(size_t n, uint32_t chunk_syms)
     return (n + chunk_syms - 1) / chunk_syms;
 }
 
-// every renormalisation emits at most 2 bytes per symbol (word coder: <= one u16,
-// rans_word_sse41.h:85-89; byte coder at scale_bits >= 8: state < 2^31 and
-// x_max >= 2^15 -> <= two bytes, rans_byte.h:64-70), plus the 128-byte header,
-// each stream padded to a multiple of 16.
+// A chunk stream never exceeds 512 + 2 * symbols bytes, whatever the coder: the word coder emits
+// <= one u16 per symbol (rans_word_sse41.h:85-89) after a 128-byte header; the byte coders emit
+// <= two bytes per symbol at scale_bits <= 16 (state < 2^31, x_max >= 2^15; rans_byte.h:64-70);
+// rans64 emits one u32 per 32 bits of information, <= scale_bits/8 <= 2 bytes per symbol plus at
+// most one extra word per lane, after a 256-byte header.  Streams are padded to multiples of 16.
 extern "C" size_t rb200_encode_bound(size_t n, uint32_t chunk_syms)
 {
     if (!chunk_syms) return 0;
     const size_t full = n / chunk_syms, tail = n % chunk_syms;
-    size_t b = full * round16(kHeaderBytes + 2ull * chunk_syms);
-    if (tail) b += round16(kHeaderBytes + 2ull * tail);
+    size_t b = full * round16(kBoundFixed + 2ull * chunk_syms);
+    if (tail) b += round16(kBoundFixed + 2ull * tail);
     return b;
 }
 
@@ -443,10 +475,18 @@ int encode_device(rb200_ctx* ctx, const rb200_model* model, const uint8_t* d_in,
             word_encode_kernel<<<grid, kEncWarps * 32, kEncSmemBytes, ctx->stream>>>(d_in, n, chunk_syms, n_chunks, model->d_word_enc,
                                                                                       scratch, slot, sizes, ctx->d_status);
             rc = check_launch(ctx, "word_encode_kernel");
-        } else {
+        } else if (model->coder == RB200_CODER_ALIAS) {
             rc = launch_alias_encode(ctx->stream, d_in, n, chunk_syms, n_chunks, model->scale_bits, model->d_alias_enc,
                                      model->d_alias_remap, scratch, slot, sizes, ctx->d_status);
             if (rc == RB200_OK) rc = check_launch(ctx, "alias_encode_kernel");
+        } else if (model->coder == RB200_CODER_BYTE) {
+            rc = launch_alias_encode(ctx->stream, d_in, n, chunk_syms, n_chunks, model->scale_bits, model->d_byte_enc, nullptr, scratch,
+                                     slot, sizes, ctx->d_status);
+            if (rc == RB200_OK) rc = check_launch(ctx, "byte_encode_kernel");
+        } else {
+            launch_rans64_encode(ctx->stream, d_in, n, chunk_syms, n_chunks, model->scale_bits, model->d_r64_enc, scratch, slot, sizes,
+                                 ctx->d_status);
+            rc = check_launch(ctx, "rans64_encode_kernel");
         }
         if (rc != RB200_OK) return rc;
     }
@@ -469,6 +509,16 @@ int decode_device(rb200_ctx* ctx, const rb200_model* model, const uint8_t* d_blo
             word_decode_kernel<false><<<grid, kDecWarps * 32, 0, ctx->stream>>>(d_blob, blob_size, d_offsets, model->d_word_dec, d_out,
                                                                                  n, chunk_syms, n_chunks, ctx->d_status);
         return check_launch(ctx, "word_decode_kernel");
+    }
+    if (model->coder == RB200_CODER_RANS64) {
+        launch_rans64_decode(ctx->stream, d_blob, blob_size, d_offsets, model->scale_bits, model->d_r64_dec, d_out, n, chunk_syms,
+                             n_chunks, ctx->d_status);
+        return check_launch(ctx, "rans64_decode_kernel");
+    }
+    if (model->coder == RB200_CODER_BYTE) {
+        launch_byte_decode(ctx->stream, d_blob, blob_size, d_offsets, model->scale_bits, model->d_byte_dec, d_out, n, chunk_syms,
+                           n_chunks, ctx->d_status);
+        return check_launch(ctx, "byte_decode_kernel");
     }
     int rc = launch_alias_decode(ctx->stream, d_blob, blob_size, d_offsets, model->scale_bits, model->d_alias_dec, d_out, n,
                                  chunk_syms, n_chunks, ctx->d_status);

@@ -46,4 +46,29 @@ struct AliasDeviceTables {
 };
 int build_alias_device_tables(const uint32_t freqs[256], uint32_t scale_bits, AliasDeviceTables& t);
 
+// ---- byte coder with cum2sym (main.cpp semantics over rans_byte.h), scale_bits 8..16
+//
+// decode: cum2sym[1 << scale_bits] (main.cpp:145-148) followed by 256 x u32 {start | freq << 16}
+//   (= RansDecSymbol, rans_byte.h:168-171; like the reference's u16 field, freq must be < 65536).
+// encode: RansEncSymbol images (rans_byte.h:159-165, built as RansEncSymbolInit :174-243 does)
+//   stored in AliasEncEntry's four words: {x_max, rcp_freq, bias, cmpl_freq | rcp_shift << 16}.
+struct ByteDeviceTables {
+    uint32_t scale_bits;
+    std::vector<uint8_t> dec;          // (1 << scale_bits) + 1024 bytes
+    AliasEncEntry enc[256];
+};
+int build_byte_device_tables(const uint32_t freqs[256], uint32_t scale_bits, ByteDeviceTables& t);
+
+// ---- rans64 (main64.cpp semantics over rans64.h), scale_bits 8..16
+//
+// decode: cum2sym[1 << scale_bits] followed by 256 x {u32 start, u32 freq} (= Rans64DecSymbol, rans64.h:151-154)
+// encode: 256 x 32 B: {rcp_lo, rcp_hi, freq, bias}, {cmpl_freq, rcp_shift, 0, 0} (= Rans64EncSymbol, rans64.h:142-148,
+//   built as Rans64EncSymbolInit :167-247 does); bit 31 of rcp_shift marks a symbol outside the model.
+struct Rans64DeviceTables {
+    uint32_t scale_bits;
+    std::vector<uint8_t> dec;          // (1 << scale_bits) + 2048 bytes
+    uint32_t enc[256][8];
+};
+int build_rans64_device_tables(const uint32_t freqs[256], uint32_t scale_bits, Rans64DeviceTables& t);
+
 }  // namespace rb200

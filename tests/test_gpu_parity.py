@@ -11,7 +11,7 @@ import oracle as orc
 
 pytestmark = pytest.mark.gpu
 
-WORD, ALIAS = 0, 2
+WORD, BYTE, ALIAS, RANS64 = 0, 1, 2, 3
 
 
 def _model(oracle_lib, data, scale_bits):
@@ -141,6 +141,49 @@ def test_alias_corrupt_stream_is_reported(gpu_ctx, oracle_lib, gen):
     with pytest.raises(rb.RansError) as ei:
         gpu_ctx.decode_host(model, bad, offs, data.size, 4096)
     assert ei.value.code == -4
+
+
+# ---------------------------------------------------------------- rans_byte cum2sym coder (main.cpp) and rans64 (main64.cpp)
+
+@pytest.mark.parametrize("kind", ["zipf", "uniform", "text", "two", "const", "skew"])
+@pytest.mark.parametrize("n,chunk,sb", [(1, 32, 14), (33, 64, 14), (4096, 4096, 14), (100003, 4096, 14), (300000, 16384, 14),
+                                        (50001, 2048, 12), (50001, 2048, 8), (70001, 8192, 16)])
+def test_byte_parity(gpu_ctx, oracle_lib, gen, kind, n, chunk, sb):
+    if kind == "const" and sb == 16:
+        pytest.skip("a frequency of 65536 does not fit the reference's 16-bit RansDecSymbol.freq")
+    data = gen(kind, n, seed=n * 13 + len(kind))
+    _roundtrip(gpu_ctx, oracle_lib, data, BYTE, sb, chunk)
+
+
+def test_byte_rejects_16bit_overflow(gpu_ctx, gen):
+    import ryg_rans_b200 as rb
+    freqs = np.zeros(256, np.uint32)
+    freqs[65] = 65536
+    with pytest.raises(rb.RansError) as ei:
+        gpu_ctx.model(BYTE, 16, freqs)
+    assert ei.value.code == -2
+
+
+@pytest.mark.parametrize("kind", ["zipf", "uniform", "text", "two", "const", "skew"])
+@pytest.mark.parametrize("n,chunk,sb", [(1, 32, 14), (33, 64, 14), (4096, 4096, 14), (100003, 4096, 14), (300000, 16384, 14),
+                                        (50001, 2048, 8), (70001, 8192, 16)])
+def test_rans64_parity(gpu_ctx, oracle_lib, gen, kind, n, chunk, sb):
+    data = gen(kind, n, seed=n * 17 + len(kind))
+    _roundtrip(gpu_ctx, oracle_lib, data, RANS64, sb, chunk)
+
+
+@pytest.mark.parametrize("coder,ocoder,sb", [(BYTE, orc.CODER_BYTE, 14), (RANS64, orc.CODER_RANS64, 14)])
+def test_byte_and_rans64_reference_stream_n32(gpu_ctx, ref_lib, gen, coder, ocoder, sb):
+    """The reference's own RansEncPutSymbol / Rans64EncPutSymbol loops (N = 32) produce the GPU's chunk stream,
+    and the reference's decoders read the GPU stream."""
+    data = gen("text", 60000, 8)
+    freqs, cum = ref_lib.model(data, sb)
+    ref_stream = ref_lib.encode(ocoder, data, freqs, cum, 32, sb)
+    model = gpu_ctx.model(coder, sb, freqs)
+    blob, offs = gpu_ctx.encode_host(model, data, 1 << 16)
+    assert np.array_equal(blob[int(offs[0]):], ref_stream)
+    dec, used = ref_lib.decode(ocoder, blob[int(offs[0]):], data.size, freqs, cum, 32, sb)
+    assert np.array_equal(dec, data) and used == ref_stream.size
 
 
 # ---------------------------------------------------------------- device histogram / per-block models (config 5)

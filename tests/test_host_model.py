@@ -38,9 +38,9 @@ def test_geometry_calls():
     assert lib.dll.rb200_chunk_count(0, 4096) == 0
     assert lib.dll.rb200_chunk_count(1, 4096) == 1
     assert lib.dll.rb200_chunk_count(8193, 4096) == 3
-    # bound = per chunk round16(128 + 2 * m)
-    assert lib.dll.rb200_encode_bound(4096, 4096) == 128 + 8192
-    assert lib.dll.rb200_encode_bound(4097, 4096) == 128 + 8192 + 144
+    # bound = per chunk round16(512 + 2 * m), valid for every coder
+    assert lib.dll.rb200_encode_bound(4096, 4096) == 512 + 8192
+    assert lib.dll.rb200_encode_bound(4097, 4096) == 512 + 8192 + 528
     assert lib.dll.rb200_encode_bound(0, 4096) == 0
 
 
