@@ -154,6 +154,29 @@ int rb200_blocks_decode(rb200_ctx* ctx, const uint8_t* blob, size_t blob_size, c
                         const uint16_t* block_freqs, uint32_t n_blocks, uint32_t block_size,
                         uint32_t chunk_syms, uint8_t* out, int mem_kind);
 
+/* ---------------------------------------------------------------- wire format (host only) */
+
+/* Self-describing envelope around (freqs, offsets, blob): versioned 64-byte header (coder, scale_bits,
+ * lanes, chunk_syms, n, n_chunks, blob size), the model, the directory, the blob; CRC-32 over header +
+ * model + directory always, over the blob when RB200_CONTAINER_CRC_BLOB is given.  The reference has
+ * nothing comparable (it keeps a pointer, main.cpp:182-188).  rb200_container_open validates and
+ * returns pointers INTO buf (which must be 8-byte aligned; the blob then sits 16-byte aligned). */
+#define RB200_CONTAINER_CRC_BLOB 1u
+
+typedef struct rb200_container_info {
+    uint32_t coder, scale_bits, chunk_syms, flags;
+    uint64_t n_symbols, n_chunks, blob_bytes;
+    const uint32_t* freqs;      /* 256 */
+    const uint64_t* offsets;    /* n_chunks + 1 */
+    const uint8_t* blob;
+} rb200_container_info;
+
+size_t rb200_container_size(size_t n_chunks, size_t blob_bytes);
+int rb200_container_pack(int coder, uint32_t scale_bits, uint32_t chunk_syms, size_t n, const uint32_t freqs[256],
+                         const uint64_t* offsets, const uint8_t* blob, size_t blob_bytes, uint32_t flags,
+                         uint8_t* out, size_t out_cap, size_t* out_size);
+int rb200_container_open(const uint8_t* buf, size_t size, rb200_container_info* info);
+
 #ifdef __cplusplus
 }
 #endif

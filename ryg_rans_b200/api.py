@@ -43,7 +43,48 @@ EXPORTS = [
                                       C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t), C.c_int]),
     ("rb200_blocks_decode", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
                                       C.c_uint32, C.c_void_p, C.c_int]),
+    ("rb200_container_size", C.c_size_t, [C.c_size_t, C.c_size_t]),
+    ("rb200_container_pack", C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.c_size_t, _u32p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                       C.c_uint32, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    ("rb200_container_open", C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p]),
 ]
+CONTAINER_CRC_BLOB = 1
+
+
+class ContainerInfo(C.Structure):
+    _fields_ = [("coder", C.c_uint32), ("scale_bits", C.c_uint32), ("chunk_syms", C.c_uint32), ("flags", C.c_uint32),
+                ("n_symbols", C.c_uint64), ("n_chunks", C.c_uint64), ("blob_bytes", C.c_uint64),
+                ("freqs", _u32p), ("offsets", _u64p), ("blob", _u8p)]
+
+
+def container_pack(coder, scale_bits, chunk_syms, n, freqs, offsets, blob, flags=0):
+    lib = load()
+    freqs = np.ascontiguousarray(freqs, dtype=np.uint32)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    blob = np.ascontiguousarray(blob, dtype=np.uint8)
+    total = int(lib.dll.rb200_container_size(offsets.size - 1, blob.size))
+    out = np.zeros(total, np.uint8)
+    size = C.c_size_t(0)
+    lib.check(lib.dll.rb200_container_pack(coder, scale_bits, chunk_syms, n, freqs.ctypes.data_as(_u32p), offsets.ctypes.data,
+                                           blob.ctypes.data, blob.size, flags, out.ctypes.data, total, C.byref(size)))
+    return out[:size.value]
+
+
+def container_open(buf):
+    """Returns (info dict, freqs, offsets, blob) as numpy views into buf."""
+    lib = load()
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    info = ContainerInfo()
+    lib.check(lib.dll.rb200_container_open(buf.ctypes.data, buf.size, C.byref(info)))
+    base = buf.ctypes.data
+    f_off = C.addressof(info.freqs.contents) - base
+    o_off = C.addressof(info.offsets.contents) - base
+    b_off = (C.addressof(info.blob.contents) - base) if info.blob_bytes else buf.size
+    freqs = buf[f_off:f_off + 1024].view(np.uint32)
+    offsets = buf[o_off:o_off + 8 * (info.n_chunks + 1)].view(np.uint64)
+    blob = buf[b_off:b_off + info.blob_bytes]
+    meta = {k: int(getattr(info, k)) for k in ("coder", "scale_bits", "chunk_syms", "flags", "n_symbols", "n_chunks", "blob_bytes")}
+    return meta, freqs, offsets, blob
 
 
 class RansError(RuntimeError):

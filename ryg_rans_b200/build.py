@@ -42,7 +42,7 @@ def build(force=False, verbose=False):
     nvcc = _nvcc()
     if force or _stale(LIB_PATH):
         cmd = [nvcc, *NVCC_FLAGS, "-shared", "-o", LIB_PATH,
-               os.path.join(CSRC, "rans_b200.cu"), os.path.join(CSRC, "model_host.cpp")]
+               os.path.join(CSRC, "rans_b200.cu"), os.path.join(CSRC, "model_host.cpp"), os.path.join(CSRC, "container_host.cpp")]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         subprocess.check_call(cmd)

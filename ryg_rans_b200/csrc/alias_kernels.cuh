@@ -290,8 +290,10 @@ alias_encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_s
         if (ALIAS) s_tab[i] = (e.shift & kEncBadSymbol) ? make_uint4(0, 1, 0, kEncBadSymbol) : make_uint4(e.magic, e.freq, e.cum, e.shift);
         else       s_tab[i] = make_uint4(e.magic, e.freq, e.cum, e.shift);          // the host already made bad entries safe
     }
-    const uint32_t remap_vecs = ALIAS ? (2u << sb) / 16 : 0;
-    for (uint32_t i = threadIdx.x; i < remap_vecs; i += blockDim.x) s_remap[i] = reinterpret_cast<const uint4*>(g_remap)[i];
+    if (ALIAS) {
+        const uint32_t remap_vecs = (2u << sb) / 16;
+        for (uint32_t i = threadIdx.x; i < remap_vecs; i += blockDim.x) s_remap[i] = reinterpret_cast<const uint4*>(g_remap)[i];
+    }
     __syncthreads();
 
     const uint32_t warp = threadIdx.x >> 5;

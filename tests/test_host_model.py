@@ -119,3 +119,29 @@ def test_alias_tables_match_oracle_other_scales(oracle_lib, gen, sb):
     got = (st.divider, st.slot_adjust, st.slot_freqs, st.sym_id, st.alias_remap)
     for g, w in zip(got, want):
         assert np.array_equal(g, w)
+
+
+def test_container_pack_open_roundtrip(oracle_lib, gen):
+    """the wire format carries coder, scale_bits, lanes, chunk size, n, model, directory, checksums."""
+    from ryg_rans_b200 import api
+    data = gen("zipf", 50000, 4)
+    freqs, cum = oracle_lib.model(data, 12)
+    blob, offs = oracle_lib.chunked_encode(orc.CODER_WORD, data, freqs, cum, 4096)     # the oracle stands in for the GPU here
+    for flags in (0, api.CONTAINER_CRC_BLOB):
+        buf = api.container_pack(rb.CODER_WORD, 12, 4096, data.size, freqs, offs, blob, flags)
+        assert buf.size == 64 + 1024 + 8 * offs.size + (-(64 + 1024 + 8 * offs.size) % 16) + blob.size
+        meta, f2, o2, b2 = api.container_open(buf)
+        assert meta == {"coder": 0, "scale_bits": 12, "chunk_syms": 4096, "flags": flags, "n_symbols": data.size,
+                        "n_chunks": offs.size - 1, "blob_bytes": blob.size}
+        assert np.array_equal(f2, freqs) and np.array_equal(o2, offs) and np.array_equal(b2, blob)
+        out = oracle_lib.chunked_decode(orc.CODER_WORD, b2, o2, data.size, f2, np.concatenate([[0], np.cumsum(f2)]).astype(np.uint32), 4096)
+        assert np.array_equal(out, data)
+        # corruption of header, model, directory (always) and payload (when its CRC is on) is detected
+        for pos in (5, 70, 64 + 1024 + 9) + ((buf.size - 7,) if flags else ()):
+            bad = buf.copy()
+            bad[pos] ^= 0x40
+            with pytest.raises(rb.RansError) as ei:
+                api.container_open(bad)
+            assert ei.value.code == -4
+    with pytest.raises(rb.RansError):
+        api.container_open(buf[:200])
