@@ -155,6 +155,19 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def ncu_traffic(workload, chunk, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json), or None when no capture exists for this workload/chunk."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)
+        if t["workload"] == workload and t["chunk_syms"] == chunk:
+            return t["dram_bytes_per_launch"].get(kernel)
+    except Exception:
+        pass
+    return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -411,7 +424,8 @@ def run_ours(args, rank, local_rank, world):
         "decode_ms": dec_ms_max, "encode_ms": enc_ms_max,
         "roofline": {"kernel": {"word": "word_decode_kernel", "alias": "alias_decode_kernel", "blocks": "block_decode_kernel"}[coder_name],
                      "bound": "hbm",
-                     "achieved": dec_gbs, "peak": peak, "unit": "GB/s", "frac": dec_gbs / peak, "traffic": None,
+                     "achieved": dec_gbs, "peak": peak, "unit": "GB/s", "frac": dec_gbs / peak,
+                     "traffic": ncu_traffic(args.workload, chunk, "word_decode_kernel") if n == 1 << 30 else None,
                      "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src},
         "roofline_encode_call": {"kernels": "encode + directory_scan + compact", "bound": "hbm", "achieved": enc_gbs, "peak": peak,
                                  "unit": "GB/s", "frac": enc_gbs / peak, "algorithmic_bytes_per_call": algo_bytes},

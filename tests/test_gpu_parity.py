@@ -327,3 +327,52 @@ def test_full_size_roundtrip_properties(gpu_ctx, coder, sb, kind):
     model.close()
     del data, blob, out, offsets
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("coder,sb", [(WORD, 12), (BYTE, 14), (ALIAS, 16), (RANS64, 14)])
+@pytest.mark.parametrize("chunk", [1000, 4104])
+def test_unaligned_chunk_sizes(gpu_ctx, oracle_lib, gen, coder, sb, chunk):
+    """chunk_syms that are not multiples of 16: chunk starts are unaligned, so the encoders' 128-bit staging
+    falls back to byte loads and ragged tails appear in every chunk."""
+    data = gen("zipf", 23456, seed=chunk)
+    _roundtrip(gpu_ctx, oracle_lib, data, coder, sb, chunk)
+
+
+def test_device_pointers_with_offset_views(gpu_ctx, oracle_lib, gen):
+    """DEVICE mode on sub-buffers: input at an odd device address (unaligned staging path), outputs 16-byte aligned."""
+    import torch
+    data = gen("text", 70001, 31)
+    freqs, cum = _model(oracle_lib, data, 12)
+    model = gpu_ctx.model(WORD, 12, freqs)
+    d_all = torch.zeros(data.size + 64, dtype=torch.uint8, device="cuda")
+    d_in = d_all[3:3 + data.size]
+    d_in.copy_(torch.from_numpy(data))
+    n_chunks = gpu_ctx.chunk_count(data.size, 4096)
+    cap = gpu_ctx.encode_bound(data.size, 4096)
+    blob = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+    offs = torch.zeros(n_chunks + 1, dtype=torch.int64, device="cuda")
+    out = torch.zeros(data.size + 7, dtype=torch.uint8, device="cuda")
+    gpu_ctx.encode_device(model, d_in.data_ptr(), data.size, 4096, blob.data_ptr(), cap, offs.data_ptr())
+    gpu_ctx.sync()
+    size = int(offs[-1])
+    oblob, ooffs = oracle_lib.chunked_encode(orc.CODER_WORD, data, freqs, cum, 4096)
+    assert np.array_equal(blob[:size].cpu().numpy(), oblob) and np.array_equal(offs.cpu().numpy().astype(np.uint64), ooffs)
+    gpu_ctx.decode_device(model, blob.data_ptr(), size, offs.data_ptr(), 4096, out[5:].data_ptr(), data.size)
+    gpu_ctx.sync()
+    assert np.array_equal(out[5:5 + data.size].cpu().numpy(), data)
+    model.close()
+
+
+@pytest.mark.parametrize("coder", ["word", "alias"])
+def test_cpp_driver_exam_gpu(coder):
+    """The reference-style C++ driver (csrc/exam_gpu.cpp) over the C-ABI: host code in C++, no Python in the path."""
+    import os
+    import subprocess
+    import ryg_rans_b200 as rb
+    rb.build()
+    exe = os.path.join(os.path.dirname(rb.LIB_PATH), "exam_gpu")
+    assert os.path.exists(exe)
+    out = subprocess.run([exe, "-", coder, "8192", str(8 << 20)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert "decode ok!" in out.stdout and "ERROR" not in out.stdout
+    assert "GPU rANS:" in out.stdout
