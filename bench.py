@@ -356,6 +356,8 @@ def run_ours(args, rank, local_rank, world):
     if dist:
         from ryg_rans_b200.shard import gather_blobs
         g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
+        gblob, gdir = gather_blobs(blob[:blob_size], offsets, dst=0)       # warm-up: NCCL channel set-up, allocations
+        del gblob, gdir
         dist.barrier(); torch.cuda.synchronize()
         g0.record()
         gblob, gdir = gather_blobs(blob[:blob_size], offsets, dst=0)

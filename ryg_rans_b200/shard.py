@@ -21,7 +21,10 @@ def gather_blobs(blob, offsets, dst=0, group=None):
     """blob: 1-D uint8 tensor holding this rank's container (size = offsets[-1], a multiple
     of 16); offsets: 1-D int64 tensor [n_chunks + 1].  Returns on `dst` the concatenated
     container and its global directory (offsets shifted by the preceding blob sizes, a valid
-    rb200 directory because every blob ends 16-byte aligned); elsewhere (None, None)."""
+    rb200 directory because every blob ends 16-byte aligned); elsewhere (None, None).
+
+    One all_gather of the sizes, then exact-size point-to-point transfers straight into their
+    final position in the destination buffers (no padding, no staging copies)."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     dev = blob.device
@@ -31,25 +34,37 @@ def gather_blobs(blob, offsets, dst=0, group=None):
     sizes = [int(t[0]) for t in allsz]
     n_offs = [int(t[1]) for t in allsz]
     assert all(s % 16 == 0 for s in sizes), "container invariant: every blob ends on a 16-byte boundary"
-    max_b, max_o = max(sizes), max(n_offs)
-    pad_b = torch.zeros(max_b, dtype=torch.uint8, device=dev)
-    pad_b[:blob.numel()] = blob
-    pad_o = torch.zeros(max_o, dtype=torch.int64, device=dev)
-    pad_o[:offsets.numel()] = offsets
-    if rank == dst:
-        gb = [torch.empty(max_b, dtype=torch.uint8, device=dev) for _ in range(world)]
-        go = [torch.empty(max_o, dtype=torch.int64, device=dev) for _ in range(world)]
-    else:
-        gb = go = None
-    dist.gather(pad_b, gb, dst=dst, group=group)
-    dist.gather(pad_o, go, dst=dst, group=group)
+    blob = blob.contiguous()
+    offsets = offsets.contiguous()
     if rank != dst:
+        ops = []
+        if sizes[rank]:
+            ops.append(dist.P2POp(dist.isend, blob, dst, group))
+        ops.append(dist.P2POp(dist.isend, offsets, dst, group))
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
         return None, None
-    base = 0
-    blobs, dirs = [], []
+    gblob = torch.empty(sum(sizes), dtype=torch.uint8, device=dev)
+    gdir = torch.empty(sum(n - 1 for n in n_offs) + 1, dtype=torch.int64, device=dev)
+    tmp_dirs = [torch.empty(n, dtype=torch.int64, device=dev) for n in n_offs]
+    ops, base = [], 0
     for r in range(world):
-        blobs.append(gb[r][:sizes[r]])
-        dirs.append(go[r][:n_offs[r] - 1] + base)
+        if r == dst:
+            gblob[base:base + sizes[r]] = blob
+            tmp_dirs[r].copy_(offsets)
+        else:
+            if sizes[r]:
+                ops.append(dist.P2POp(dist.irecv, gblob[base:base + sizes[r]], r, group))
+            ops.append(dist.P2POp(dist.irecv, tmp_dirs[r], r, group))
         base += sizes[r]
-    dirs.append(torch.tensor([base], dtype=torch.int64, device=dev))
-    return torch.cat(blobs), torch.cat(dirs)
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    base, pos = 0, 0
+    for r in range(world):
+        k = n_offs[r] - 1
+        gdir[pos:pos + k] = tmp_dirs[r][:k] + base
+        pos += k
+        base += sizes[r]
+    gdir[pos] = base
+    return gblob, gdir
