@@ -248,9 +248,9 @@ block_decode_kernel(const uint8_t* __restrict__ blob, uint64_t blob_size, const 
     uint8_t* dst = out + static_cast<uint64_t>(blockIdx.x) * block_size + static_cast<uint64_t>(warp) * chunk_syms;
     const uint32_t ring = smem_addr(s_dyn) + warp * kRingBytes;
     if (s_flag[1])
-        word_decode_chunk<true>(blob, blob_size, offsets, chunk, smem_addr(s_tab), ring, dst, chunk_syms, status);
+        word_decode_chunk<true>(blob, blob_size, offsets, chunk, smem_addr_pinned(s_tab), ring, dst, chunk_syms, status);
     else
-        word_decode_chunk<false>(blob, blob_size, offsets, chunk, smem_addr(s_tab), ring, dst, chunk_syms, status);
+        word_decode_chunk<false>(blob, blob_size, offsets, chunk, smem_addr_pinned(s_tab), ring, dst, chunk_syms, status);
 }
 
 __global__ void __launch_bounds__(kMaxBlockWarps * 32)

@@ -29,6 +29,14 @@ __device__ __forceinline__ uint32_t smem_addr(const void* p)
 {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+// same value, but produced by a volatile asm so the compiler keeps it in a register instead of
+// re-deriving it (S2UR SR_CgaCtaId + LEA) inside hot loops when registers are tight
+__device__ __forceinline__ uint32_t smem_addr_pinned(const void* p)
+{
+    uint32_t a;
+    asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(a) : "l"(p));
+    return a;
+}
 __device__ __forceinline__ uint32_t lds_u16(uint32_t addr)
 {
     uint16_t v;

@@ -36,10 +36,11 @@ struct StreamWindow {
     const uint4* base;      // blob, warp-uniform
     uint4 parked;           // unit in flight
 
+    // Past the end of the blob the last vector is fetched again instead: what lies beyond a stream's
+    // own end is never consumed by a valid stream, and a corrupt one may read any in-bounds bytes.
     __device__ __forceinline__ uint4 fetch()
     {
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (next_vec < limit_vec) v = ldg_stream_u128(base + next_vec);
+        const uint4 v = ldg_stream_u128(base + min(next_vec, limit_vec - 1));
         next_vec += 32;
         return v;
     }
@@ -88,22 +89,31 @@ __device__ __forceinline__ uint32_t word_table_freq(uint32_t e)
 }
 
 // one decode step for the whole warp: RansWordDecSym + RansWordDecRenorm
+__device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// one decode step for the whole warp: RansWordDecSym + RansWordDecRenorm.
+// tab = shared-space address of the packed table (kept live in a register by the caller).
 template <bool WIDE>
-__device__ __forceinline__ void word_dec_step(uint32_t& x, uint32_t& cursor, uint32_t tab /*shared addr*/, uint32_t ring,
+__device__ __forceinline__ void word_dec_step(uint32_t& x, uint32_t& cursor, uint32_t tab, uint32_t ring,
                                               uint8_t* o, uint32_t lt, bool active)
 {
     bool need = false;
     if (active) {
-        const uint32_t e = lds_u32_ro(tab + 4u * (x & (kWordSlots - 1)));       // rans_word_sse41.h:126
+        const uint32_t e = lds_u32_ro(mad_u32(x & (kWordSlots - 1), 4u, tab));  // rans_word_sse41.h:126
         x = word_table_freq<WIDE>(e) * (x >> kWordScaleBits) + ((e >> 8) & 0xfffu);   // :129
         *o = static_cast<uint8_t>(e);                                       // :130
         need = x < kWordL;                                                  // :137
     }
     const uint32_t mask = __ballot_sync(0xffffffffu, need);
-    const uint32_t a = cursor + 2u * __popc(mask & lt);                     // lane order within the step
+    const uint32_t a = mad_u32(__popc(mask & lt), 2u, cursor);              // lane order within the step
     const uint32_t w = lds_u16(ring | (a & (kRingBytes - 1)));
     if (need) x = (x << 16) | w;                                            // :138
-    cursor += 2u * __popc(mask);                                            // :139
+    cursor = mad_u32(__popc(mask), 2u, cursor);                             // :139
 }
 
 // Decode chunk `chunk` (one warp).  tab = shared address of the 4096-entry packed table,
@@ -188,7 +198,7 @@ word_decode_kernel(const uint8_t* __restrict__ blob, uint64_t blob_size, const u
     if (chunk >= n_chunks) return;
     const uint64_t first = static_cast<uint64_t>(chunk) * chunk_syms;
     const uint32_t m = static_cast<uint32_t>(min(static_cast<uint64_t>(chunk_syms), n - first));
-    word_decode_chunk<WIDE>(blob, blob_size, offsets, chunk, smem_addr(s_tab), smem_addr(&s_ring[warp][0]), out + first, m, status);
+    word_decode_chunk<WIDE>(blob, blob_size, offsets, chunk, smem_addr_pinned(s_tab), smem_addr(&s_ring[warp][0]), out + first, m, status);
 }
 
 // ---------------------------------------------------------------------------
