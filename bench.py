@@ -421,7 +421,9 @@ def run_ours(args, rank, local_rank, world):
         "config": {"workload": args.workload, "symbols_per_gpu": n, "chunk_syms": chunk, "lanes": 32, "coder": coder_name,
                    "scale_bits": sb, "compressed_bytes_per_symbol": blob_size / n,
                    "l2": "inputs (1 GiB symbols + ~1 GiB blob) exceed the 126 MB L2; no flush needed",
-                   "step": ("per-block models (1 launch) + " if blocks else "") + "encode (3 launches) + decode (1 launch), device-resident"},
+                   "step": ("per-block models (1 launch) + encode (3 launches)" if blocks else
+                            ("encode (3 launches)" if coder_name != "word" or chunk < 4096 else "encode (1 fused launch)"))
+                           + " + decode (1 launch), device-resident"},
         "decode_gsym_s": world * n / (dec_ms_max * 1e-3) / 1e9, "encode_gsym_s": world * n / (enc_ms_max * 1e-3) / 1e9,
         "decode_ms": dec_ms_max, "encode_ms": enc_ms_max,
         "roofline": {"kernel": {"word": "word_decode_kernel", "alias": "alias_decode_kernel", "blocks": "block_decode_kernel"}[coder_name],

@@ -414,18 +414,21 @@ int reserve_encode_workspace(rb200_ctx* ctx, uint32_t n_chunks, uint32_t slot, u
     return RB200_OK;
 }
 
-// default: three kernels (encode into per-chunk slots, tile scan, compaction).  RB200_ENCODE_PATH=fused
-// selects the single persistent launch with decoupled look-back; measured slower on B200 in round 1
-// (1.69 ms vs 1.59 ms per GiB: the look-back polling costs more than the saved pass, profiles/), kept
-// for experiments and covered by tests/test_gpu_parity.py::test_fused_encode_path.
-bool use_fused_encode()
+// Word-coder encode has two paths:
+//   fused: ONE persistent launch -- workers encode, a scanner warp turns published sizes into end offsets
+//          in chunk order, workers place chunk k after encoding chunk k+1 (word_kernels.cuh, K2f);
+//   split: three launches -- encode into per-chunk worst-case slots, tile scan, compaction.
+// fused is ~10 % faster per GiB on B200 (1.43 vs 1.58 ms) as long as the scanner keeps up, i.e. for
+// chunks of >= 4096 symbols; below that the split path is used.  RB200_ENCODE_PATH=split|fused forces one.
+bool use_fused_encode(uint32_t chunk_syms)
 {
-    static int v = -1;
-    if (v < 0) {
+    static int forced = -2;
+    if (forced == -2) {
         const char* e = std::getenv("RB200_ENCODE_PATH");
-        v = (e && std::strcmp(e, "fused") == 0) ? 1 : 0;
+        forced = !e ? -1 : (std::strcmp(e, "fused") == 0 ? 1 : (std::strcmp(e, "split") == 0 ? 0 : -1));
     }
-    return v == 1;
+    if (forced >= 0) return forced == 1;
+    return chunk_syms >= 4096;
 }
 
 int sm_count(int device)
@@ -442,10 +445,10 @@ int encode_word_fused(rb200_ctx* ctx, const rb200_model* model, const uint8_t* d
                       uint8_t* d_blob, size_t blob_cap, uint64_t* d_offsets)
 {
     const uint32_t slot = slot_bytes_for(chunk_syms);
-    const uint32_t want = (n_chunks + kEncWarps - 1) / kEncWarps;
+    const uint32_t want = (n_chunks + 1 + kEncWarps - 1) / kEncWarps;       // + 1: one warp of the grid is the scanner
     uint32_t grid = static_cast<uint32_t>(sm_count(ctx->device)) * RB200_ENC_MINBLOCKS;
     if (grid > want) grid = want;
-    int rc = reserve(ctx, ctx->scratch, static_cast<size_t>(grid) * kEncWarps * slot + 16);      // one slot per resident warp
+    int rc = reserve(ctx, ctx->scratch, static_cast<size_t>(grid) * kEncWarps * 2 * slot + 16);  // two slots per resident warp
     if (rc == RB200_OK) rc = reserve(ctx, ctx->sizes, 16 + static_cast<size_t>(n_chunks) * sizeof(uint64_t));
     if (rc != RB200_OK) return rc;
     uint32_t* counter = static_cast<uint32_t*>(ctx->sizes.p);
@@ -463,7 +466,7 @@ int encode_device(rb200_ctx* ctx, const rb200_model* model, const uint8_t* d_in,
     const size_t n_chunks_sz = rb200_chunk_count(n, chunk_syms);
     if (n_chunks_sz >= (1ull << 31)) return RB200_E_ARG;
     const uint32_t n_chunks = static_cast<uint32_t>(n_chunks_sz);
-    if (n_chunks && model->coder == RB200_CODER_WORD && use_fused_encode())
+    if (n_chunks && model->coder == RB200_CODER_WORD && use_fused_encode(chunk_syms))
         return encode_word_fused(ctx, model, d_in, n, chunk_syms, n_chunks, d_blob, blob_cap, d_offsets);
     const uint32_t slot = slot_bytes_for(chunk_syms);
     uint8_t* scratch; uint32_t* sizes; uint64_t* tile_sums;

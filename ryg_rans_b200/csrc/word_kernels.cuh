@@ -388,16 +388,16 @@ constexpr uint32_t kEncSmemBytes = kEncTableBytes + kEncWarps * kEncWarpSmem;
 // ---------------------------------------------------------------------------
 // K2f: persistent encode with the directory and the compaction fused in.
 //
-// Every warp fetches chunk ids from an atomic counter (so chunks start in order), encodes the chunk
-// into a scratch slot that belongs to the WARP (reused for each of its chunks, so the whole scratch
-// is ~resident-warps x slot and stays in L2), publishes the chunk's padded size, resolves its
-// exclusive prefix with a decoupled look-back over the chunks before it (they started earlier and
-// finish earlier, so the nearest resolved prefix is normally a few entries back), then moves its own
-// L2-hot stream to its final place in the blob and writes its directory entry.  One launch, no CTA
-// barrier in the loop, no second pass over the compressed bytes.
+// Every worker warp fetches chunk ids from an atomic counter (so chunks start in order), encodes the
+// chunk into one of two scratch slots that belong to the WARP and publishes its padded size.  One
+// scanner warp turns the published sizes into end offsets in chunk order.  A worker places chunk k
+// (moves its stream to blob[E_k - size .. E_k) and writes the directory entry) only after it has
+// encoded chunk k+1, so its E_k is ready and no warp polls.  One launch, no CTA barrier in the loop.
+// (Two earlier variants -- per-CTA and per-warp decoupled look-back -- were correct but slower than the
+// split path because of polling)
 // ---------------------------------------------------------------------------
 constexpr uint64_t kLookAgg = 1ull << 62, kLookPrefix = 2ull << 62, kLookValue = (1ull << 62) - 1;
-constexpr uint32_t kLookSpinLimit = 1u << 26;     // a bug must not hang the GPU: give up and flag instead
+constexpr uint32_t kLookSpinLimit = 1u << 22;     // a bug must not hang the GPU: give up (after ~0.5 s) and flag instead
 
 __device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t* p)
 {
@@ -416,37 +416,6 @@ __device__ __forceinline__ uint4 ldg_l2_u128(const uint4* p)      // L2-coherent
     return v;
 }
 
-// exclusive prefix (sum of the padded sizes of all groups before `group`), computed by one warp
-__device__ __forceinline__ uint64_t lookback_exclusive(const uint64_t* look, uint32_t group, uint32_t lane, uint32_t* status)
-{
-    uint64_t excl = 0;
-    int64_t g = group;
-    while (g > 0) {
-        const int64_t idx = g - 1 - static_cast<int64_t>(lane);        // lane 0 looks at the nearest predecessor
-        uint64_t v;
-        uint32_t first, spins = 0;
-        for (;;) {
-            v = idx >= 0 ? ld_relaxed_u64(look + idx) : kLookPrefix;
-            const uint32_t flag = static_cast<uint32_t>(v >> 62);
-            const uint32_t pmask = __ballot_sync(0xffffffffu, flag == 2);
-            const uint32_t imask = __ballot_sync(0xffffffffu, flag == 0);
-            first = pmask ? static_cast<uint32_t>(__ffs(pmask)) - 1 : 32u;
-            const uint32_t needed = first >= 31 ? 0xffffffffu : ((2u << first) - 1);
-            if (!(imask & needed)) break;
-            if (++spins > kLookSpinLimit) {
-                if (lane == 0) atomicOr(status, kStatStream);
-                return excl;
-            }
-        }
-        uint64_t c = (lane <= first) ? (v & kLookValue) : 0;
-        for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-        excl += c;
-        if (first < 32) break;
-        g -= 32;
-    }
-    return excl;
-}
-
 // move one finished stream (it ends at src_end, 16-byte aligned) to blob[end - size .. end)
 __device__ __forceinline__ void place_stream(const uint8_t* src_end, uint32_t size, uint8_t* __restrict__ blob, uint64_t end, uint32_t lane)
 {
@@ -462,9 +431,103 @@ __device__ __forceinline__ void place_stream(const uint8_t* src_end, uint32_t si
     const uint4* s4 = reinterpret_cast<const uint4*>(src + (16 - gap));
     uint4* d4 = reinterpret_cast<uint4*>(dst_vec0 + 16);
     const uint32_t nvec = padded / 16 - 1;
-    for (uint32_t v = lane; v < nvec; v += 32) stg_stream_u128(d4 + v, ldg_l2_u128(s4 + v));
+    uint32_t v = lane;
+    for (; v + 96 < nvec; v += 128) {                      // four loads in flight per lane: the scratch is mostly in HBM by now
+        const uint4 a = ldg_l2_u128(s4 + v), b = ldg_l2_u128(s4 + v + 32), c = ldg_l2_u128(s4 + v + 64), d = ldg_l2_u128(s4 + v + 96);
+        stg_stream_u128(d4 + v, a);
+        stg_stream_u128(d4 + v + 32, b);
+        stg_stream_u128(d4 + v + 64, c);
+        stg_stream_u128(d4 + v + 96, d);
+    }
+    for (; v < nvec; v += 32) stg_stream_u128(d4 + v, ldg_l2_u128(s4 + v));
 }
 
+// The scanner: ONE warp of the grid walks the status array in chunk order and rewrites every published
+// size (kLookAgg | padded size) into the inclusive end offset E_c (kLookPrefix | E_c).  Chunks are handed
+// out in order, so the entry it waits for always belongs to a chunk some resident warp is encoding.
+__device__ __forceinline__ void fused_scanner(uint64_t* look, uint32_t n_chunks, uint32_t lane, uint32_t* status)
+{
+    constexpr int kPer = 8;                 // consecutive entries per lane: 256 entries per trip, one warp scan per trip
+    uint64_t run = 0;
+    uint32_t pos = 0, idle = 0;
+    while (pos < n_chunks) {
+        const uint32_t base = pos + kPer * lane;
+        uint64_t v[kPer];
+#pragma unroll
+        for (int j = 0; j < kPer; j++) v[j] = (base + j < n_chunks) ? ld_relaxed_u64(look + base + j) : 0;   // independent loads
+        // r = length of this lane's leading run of published entries; local inclusive sums over that run
+        uint32_t r = 0;
+        uint64_t sum[kPer];
+        uint64_t acc = 0;
+        bool open = true;
+#pragma unroll
+        for (int j = 0; j < kPer; j++) {
+            open = open && ((v[j] >> 62) == 1);
+            if (open) { acc += v[j] & kLookValue; r = j + 1; }
+            sum[j] = acc;
+        }
+        // the contiguous ready prefix of the whole window: all of lanes < f, the first r_f entries of lane f
+        const uint32_t full = __ballot_sync(0xffffffffu, r == kPer);
+        const uint32_t f = full == 0xffffffffu ? 32u : static_cast<uint32_t>(__ffs(~full)) - 1u;
+        const uint32_t cnt = lane < f ? kPer : (lane == f ? r : 0u);
+        const uint64_t mine = cnt ? sum[cnt - 1] : 0;
+        uint64_t incl = mine;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= static_cast<uint32_t>(d)) incl += t;
+        }
+        const uint64_t before = run + incl - mine;
+#pragma unroll
+        for (int j = 0; j < kPer; j++)
+            if (static_cast<uint32_t>(j) < cnt) st_relaxed_u64(look + base + j, kLookPrefix | (before + sum[j]));
+        run += __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t r_f = __shfl_sync(0xffffffffu, r, f & 31);
+        const uint32_t done = f == 32 ? 32u * kPer : f * kPer + r_f;
+        pos += done;
+        if (done == 0) {
+            if (++idle > kLookSpinLimit) {           // never hang the GPU: give up and flag
+                if (lane == 0) atomicOr(status, kStatStream);
+                return;
+            }
+            __nanosleep(100);
+        } else {
+            idle = 0;
+        }
+    }
+}
+
+// one warp: wait for the scanner to publish E_c of `chunk`, then move the stream and write the directory entry
+__device__ __forceinline__ void fused_place(const uint64_t* look, uint32_t chunk, uint32_t n_chunks, const uint8_t* slot_end,
+                                            uint32_t produced, uint8_t* __restrict__ blob, uint64_t blob_cap,
+                                            uint64_t* __restrict__ offsets, uint32_t lane, uint32_t* status)
+{
+    uint64_t v = 0;
+    uint32_t spins = 0;
+    for (;;) {
+        if (lane == 0) v = ld_relaxed_u64(look + chunk);
+        v = __shfl_sync(0xffffffffu, v, 0);
+        if ((v >> 62) == 2) break;
+        if (++spins > kLookSpinLimit) {
+            if (lane == 0) atomicOr(status, kStatStream);
+            return;
+        }
+        __nanosleep(100);
+    }
+    const uint64_t end = v & kLookValue;                   // E_c
+    if (lane == 0) {
+        offsets[chunk] = end - produced;
+        if (chunk == n_chunks - 1) offsets[n_chunks] = end;
+    }
+    if (end <= blob_cap) {
+        place_stream(slot_end, produced, blob, end, lane);
+    } else if (lane == 0) {
+        atomicOr(status, kStatSpace);
+    }
+}
+
+// Grid = resident capacity (SMs x RB200_ENC_MINBLOCKS CTAs).  Warp 0 of CTA 0 is the scanner, every other warp is
+// a worker with TWO scratch slots: it encodes chunk k+1 into one slot before it places chunk k from the other,
+// so by the time it asks for E_k the scanner has normally long passed k and nobody polls.
 __global__ void __launch_bounds__(kEncWarps * 32, RB200_ENC_MINBLOCKS)
 word_encode_fused_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_syms, uint32_t n_chunks,
                          const WordEncEntry* __restrict__ g_table, uint8_t* __restrict__ scratch, uint32_t slot_bytes,
@@ -477,46 +540,38 @@ word_encode_fused_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t ch
     __syncthreads();
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t tab = smem_addr(s_enc), wsm = tab + kEncTableBytes + warp * kEncWarpSmem;
-    uint8_t* slot_end = scratch + (static_cast<uint64_t>(blockIdx.x) * kEncWarps + warp + 1) * slot_bytes;   // this warp's own slot
-
-    // Stagger the first fetch over roughly one chunk-time.  All resident warps start together and a
-    // chunk costs the same everywhere, so without this every wave of ~7000 chunks would finish at once
-    // and each look-back would have to add up thousands of unresolved predecessors; staggered, chunks
-    // finish (and resolve) in id order and the nearest published prefix is a few hundred entries back.
-    {
-        const uint64_t slot = static_cast<uint64_t>(blockIdx.x) * kEncWarps + warp, slots = static_cast<uint64_t>(gridDim.x) * kEncWarps;
-        uint64_t ns = static_cast<uint64_t>(chunk_syms) * 8u * slot / slots;      // ~8 ns per symbol per warp when the SM is full
-        if (n_chunks < slots) ns = 0;                                             // fewer chunks than warps: nothing to order
-        if (ns > 1000000) ns = 1000000;
-        __nanosleep(static_cast<unsigned>(ns));
+    if (blockIdx.x == 0 && warp == 0) {                    // no CTA barrier below: warps are independent from here on
+        fused_scanner(look, n_chunks, lane, status);
+        return;
     }
-    // warps are independent from here on: no CTA barrier inside the loop
+    const uint32_t tab = smem_addr(s_enc), wsm = tab + kEncTableBytes + warp * kEncWarpSmem;
+    uint8_t* slots = scratch + (static_cast<uint64_t>(blockIdx.x) * kEncWarps + warp) * 2 * slot_bytes;   // this warp's two slots
+
+    uint32_t pend_chunk = 0, pend_size = 0, parity = 0;
+    bool pending = false;
     for (;;) {
         uint32_t chunk = 0;
-        if (lane == 0) chunk = atomicAdd(counter, 1u);     // chunks start in order, which keeps the look-back short and live
+        if (lane == 0) chunk = atomicAdd(counter, 1u);     // chunks start in order
         chunk = __shfl_sync(0xffffffffu, chunk, 0);
         if (chunk >= n_chunks) break;
         const uint64_t first = static_cast<uint64_t>(chunk) * chunk_syms;
         const uint32_t m = static_cast<uint32_t>(min(static_cast<uint64_t>(chunk_syms), n - first));
+        uint8_t* slot_end = slots + (parity + 1) * static_cast<uint64_t>(slot_bytes);
         const uint32_t produced = word_encode_stream(in + first, m, tab, wsm, slot_end, status);
-        const uint64_t padded = (produced + 15u) & ~15u;
-        if (lane == 0 && chunk) st_relaxed_u64(look + chunk, kLookAgg | padded);
-        const uint64_t excl = lookback_exclusive(look, chunk, lane, status);
-        const uint64_t end = excl + padded;                // E_c
-        if (lane == 0) {
-            st_relaxed_u64(look + chunk, kLookPrefix | end);
-            offsets[chunk] = end - produced;
-            if (chunk == n_chunks - 1) offsets[n_chunks] = end;
-        }
-        if (end <= blob_cap) {
-            __syncwarp();
-            place_stream(slot_end, produced, blob, end, lane);
-        } else if (lane == 0) {
-            atomicOr(status, kStatSpace);
-        }
+        if (lane == 0) st_relaxed_u64(look + chunk, kLookAgg | ((produced + 15u) & ~15u));
+        __syncwarp();
+        if (pending)
+            fused_place(look, pend_chunk, n_chunks, slots + (2 - parity) * static_cast<uint64_t>(slot_bytes), pend_size, blob, blob_cap,
+                        offsets, lane, status);
+        pend_chunk = chunk;
+        pend_size = produced;
+        pending = true;
+        parity ^= 1;
         __syncwarp();
     }
+    if (pending)
+        fused_place(look, pend_chunk, n_chunks, slots + (2 - parity) * static_cast<uint64_t>(slot_bytes), pend_size, blob, blob_cap,
+                    offsets, lane, status);
 }
 
 // ---------------------------------------------------------------------------

@@ -227,8 +227,10 @@ def test_block_models_and_roundtrip(gpu_ctx, oracle_lib, gen, n_blocks, block_si
 
 # ---------------------------------------------------------------- alternative paths, big sizes
 
-def test_fused_encode_path(tmp_path):
-    """RB200_ENCODE_PATH=fused (persistent encode + decoupled look-back) must produce the identical container."""
+@pytest.mark.parametrize("path", ["fused", "split"])
+def test_forced_encode_paths(tmp_path, path):
+    """Both word-encode paths (RB200_ENCODE_PATH=fused: persistent encode + scanner warp + deferred placement;
+    =split: encode, tile scan, compaction) must produce the identical container at every chunk size."""
     import os
     import subprocess
     import sys
@@ -250,7 +252,7 @@ for chunk in (4096, 32, 65536):
     assert np.array_equal(ctx.decode_host(m, blob, offs, data.size, chunk), data)
 print("fused ok", ctx.launches)
 ''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, RB200_ENCODE_PATH="fused")
+    env = dict(os.environ, RB200_ENCODE_PATH=path)
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "fused ok" in out.stdout, out.stderr[-2000:]
 
