@@ -427,6 +427,8 @@ bool use_fused_encode(uint32_t chunk_syms)
         const char* e = std::getenv("RB200_ENCODE_PATH");
         forced = !e ? -1 : (std::strcmp(e, "fused") == 0 ? 1 : (std::strcmp(e, "split") == 0 ? 0 : -1));
     }
+    // two worst-case slots per resident warp: keep that scratch below ~2 GB (chunks of <= 64 Ki symbols)
+    if (chunk_syms > 65536) return false;
     if (forced >= 0) return forced == 1;
     return chunk_syms >= 4096;
 }

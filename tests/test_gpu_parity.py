@@ -378,3 +378,11 @@ def test_cpp_driver_exam_gpu(coder):
     assert out.returncode == 0, out.stderr
     assert "decode ok!" in out.stdout and "ERROR" not in out.stdout
     assert "GPU rANS:" in out.stdout
+
+
+def test_large_chunks_use_bounded_scratch(gpu_ctx, oracle_lib, gen):
+    """chunk_syms above 64 Ki symbols must not blow up the encoder's scratch (two slots per resident warp in the
+    fused path): such geometries take the split path, whose scratch is 2x the input."""
+    data = gen("zipf", (1 << 20) + 77, 5)
+    for coder, sb in ((WORD, 12), (ALIAS, 16)):
+        _roundtrip(gpu_ctx, oracle_lib, data, coder, sb, 1 << 18)
