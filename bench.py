@@ -211,6 +211,14 @@ def cpu_reference_run(kind, coder, scale_bits, nbytes, runs, threads):
     rt = nbytes / (best["enc_s"] + best["dec_s"]) / 1e9
     detail = {k: {"encode_gsym_s": round(nbytes / v["enc_s"] / 1e9, 4), "decode_gsym_s": round(nbytes / v["dec_s"] / 1e9, 4),
                   "compressed_bytes": v["bytes"]} for k, v in paths.items()}
+    if kind_s == "reference" and threads > 1:      # single-thread figures beside the all-core ones
+        small = data[:min(nbytes, 32 << 20)]
+        st = {("main_alias.cpp 2-way alias" if coder == "alias" else "main_simd.cpp 8-way scalar enc + SSE4.1 dec"):
+              ref.cpu_baseline("alias" if coder == "alias" else "simd", small, 1, runs=2, scale_bits=scale_bits if coder == "alias" else None),
+              "main64.cpp rans64 2-way": ref.cpu_baseline("rans64", small, 1, runs=2, scale_bits=14)}
+        for k, v in st.items():
+            detail[k]["single_thread_encode_gsym_s"] = round(small.size / v["enc_s"] / 1e9, 4)
+            detail[k]["single_thread_decode_gsym_s"] = round(small.size / v["dec_s"] / 1e9, 4)
     return {"value": rt, "unit": UNIT, "cores": threads, "kind": kind_s,
             "sample": f"{nbytes >> 20} MiB of the {kind} workload, one contiguous slice per thread, best of {runs}; "
                       f"round trip = encode + decode; fastest path: {best_name}",
