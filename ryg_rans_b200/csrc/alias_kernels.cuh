@@ -37,7 +37,7 @@ __device__ __forceinline__ void alias_dec_step(uint32_t& x, uint32_t& cursor, ui
         const uint32_t xm = x & ((1u << sb) - 1);                          // main_alias.cpp:258 / rans_byte.h:127
         if (ALIAS) {
             const uint32_t bucket = xm >> (sb - 8);                        // :259
-            const uint4 e = lds_u128_ro(tab_lane + bucket * (kAliasDecReplicas * 16));
+            const uint4 e = lds_u128_ro(mad_u32(bucket, kAliasDecReplicas * 16, tab_lane));
             const bool own = xm < e.x;                                     // :261 (bucket2 = 2 * bucket + 1)
             const uint32_t fs = own ? e.z : e.y;                           // slot_freqs | sym_id << 17
             const uint32_t adj = own ? (e.w >> 16) : (e.w & 0xffffu);
@@ -55,7 +55,7 @@ __device__ __forceinline__ void alias_dec_step(uint32_t& x, uint32_t& cursor, ui
     const uint32_t m1 = __ballot_sync(0xffffffffu, n1);
     const uint32_t m2 = __ballot_sync(0xffffffffu, n2);
     uint32_t a = cursor + __popc(m1 & lt);
-    if (m2) a += __popc(m2 & lt);                                          // warp-uniform: two-byte refills are rare
+    if (m2) a += __popc(m2 & lt);                                          // warp-uniform: two-byte refills are the rarer case
     const uint32_t b0 = lds_u8(ring | (a & (kRingBytes - 1)));
     if (n1) x = (x << 8) | b0;                                             // rans_byte.h:313
     cursor += __popc(m1);
@@ -110,17 +110,31 @@ alias_decode_kernel(const uint8_t* __restrict__ blob, uint64_t blob_size, const 
     cursor += kHeaderBytes;
 
     const uint32_t lt = lanemask_lt();
-    const uint32_t tab_lane = smem_addr(s_tab) + (ALIAS ? (lane & (kAliasDecReplicas - 1)) * 16 : 0);
+    const uint32_t tab_lane = smem_addr_pinned(s_tab) + (ALIAS ? (lane & (kAliasDecReplicas - 1)) * 16 : 0);
     uint8_t* o = out + first + lane;
     const uint32_t steps = m >> 5, rem = m & 31;
     uint32_t g = 0;
-    for (; g + 4 <= steps; g += 4) {
+    for (; g + 8 <= steps; g += 8) {
+        win.top_up(cursor, lane);
+        alias_dec_step<ALIAS>(x, cursor, tab_lane, win.ring, o, lt, sb, true);
+        alias_dec_step<ALIAS>(x, cursor, tab_lane, win.ring, o + 32, lt, sb, true);
+        alias_dec_step<ALIAS>(x, cursor, tab_lane, win.ring, o + 64, lt, sb, true);
+        alias_dec_step<ALIAS>(x, cursor, tab_lane, win.ring, o + 96, lt, sb, true);
+        win.top_up(cursor, lane);
+        alias_dec_step<ALIAS>(x, cursor, tab_lane, win.ring, o + 128, lt, sb, true);
+        alias_dec_step<ALIAS>(x, cursor, tab_lane, win.ring, o + 160, lt, sb, true);
+        alias_dec_step<ALIAS>(x, cursor, tab_lane, win.ring, o + 192, lt, sb, true);
+        alias_dec_step<ALIAS>(x, cursor, tab_lane, win.ring, o + 224, lt, sb, true);
+        o += 256;
+    }
+    if (g + 4 <= steps) {
         win.top_up(cursor, lane);
         alias_dec_step<ALIAS>(x, cursor, tab_lane, win.ring, o, lt, sb, true);
         alias_dec_step<ALIAS>(x, cursor, tab_lane, win.ring, o + 32, lt, sb, true);
         alias_dec_step<ALIAS>(x, cursor, tab_lane, win.ring, o + 64, lt, sb, true);
         alias_dec_step<ALIAS>(x, cursor, tab_lane, win.ring, o + 96, lt, sb, true);
         o += 128;
+        g += 4;
     }
     win.top_up(cursor, lane);
     for (; g < steps; g++) {
@@ -201,14 +215,15 @@ __device__ __forceinline__ void alias_enc_step(AliasEncState& st, uint32_t sym, 
     }
 }
 
+// Encode m symbols (one warp) as one 32-way byte-renormalised stream ending at slot_end (16-byte aligned);
+// returns the stream size in bytes (warp-uniform).
 template <bool ALIAS>
-__device__ __forceinline__ void alias_encode_chunk(const uint8_t* __restrict__ chunk_in, uint32_t m, uint32_t chunk, uint32_t tab,
-                                                   uint32_t remap, uint32_t wsm, uint32_t sb, uint8_t* __restrict__ scratch,
-                                                   uint32_t slot_bytes, uint32_t* __restrict__ sizes, uint32_t* __restrict__ status)
+__device__ __forceinline__ uint32_t alias_encode_stream(const uint8_t* __restrict__ chunk_in, uint32_t m, uint32_t tab, uint32_t remap,
+                                                        uint32_t wsm, uint32_t sb, uint8_t* __restrict__ slot_end,
+                                                        uint32_t* __restrict__ status)
 {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t stage = wsm, ring = wsm + kEncStageBytes;
-    uint8_t* slot_end = scratch + static_cast<uint64_t>(chunk + 1) * slot_bytes;
     const uint32_t tab_lane = tab + (lane & (kEncReplicas - 1)) * 16;
     const uint32_t gt = lanemask_gt();
 
@@ -269,19 +284,25 @@ __device__ __forceinline__ void alias_encode_chunk(const uint8_t* __restrict__ c
         const uint32_t off = flushed + lane + 1;
         *(slot_end - off) = static_cast<uint8_t>(lds_u8(ring | ((0u - off) & (kEncRingBytes - 1))));
     }
-    if (lane == 0) sizes[chunk] = produced;
     if (__any_sync(0xffffffffu, (st.flags & kEncBadSymbol) != 0) && lane == 0) atomicOr(status, kStatSymbol);
+    return produced;
 }
 
 // !ALIAS: g_enc holds RansEncSymbol images {x_max, rcp_freq, bias, cmpl | shift << 16}, g_remap is unused
+// Two modes (like the word encoder):
+//   look == nullptr: chunks strided over the persistent CTAs, each into its own worst-case slot of `scratch`,
+//                    sizes[] written for the tile scan + compaction that follow;
+//   look != nullptr: fused -- chunk ids from an atomic counter, two scratch slots per warp, warp 0 of CTA 0 is the
+//                    scanner, every worker places chunk k after encoding chunk k+1 (see word_kernels.cuh, K2f).
 template <bool ALIAS>
 __global__ void __launch_bounds__(kAliasEncWarps * 32, 1)
 alias_encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_syms, uint32_t n_chunks, uint32_t sb,
                     const AliasEncEntry* __restrict__ g_enc, const uint16_t* __restrict__ g_remap,
                     uint8_t* __restrict__ scratch, uint32_t slot_bytes, uint32_t* __restrict__ sizes,
-                    uint32_t* __restrict__ status)
+                    uint64_t* __restrict__ look, uint32_t* __restrict__ counter, uint8_t* __restrict__ blob, uint64_t blob_cap,
+                    uint64_t* __restrict__ offsets, uint32_t* __restrict__ status)
 {
-    extern __shared__ __align__(1024) uint8_t s_alias[];      // [32 x 1 KiB stage+ring][32 KiB table][remap]
+    extern __shared__ __align__(1024) uint8_t s_alias[];      // [32 x 1.0 KiB stage+ring][32 KiB table][remap]
     uint4* s_tab = reinterpret_cast<uint4*>(s_alias + kAliasEncWarps * kEncWarpSmem);
     uint4* s_remap = reinterpret_cast<uint4*>(s_alias + kAliasEncFixedSmem);
     for (uint32_t i = threadIdx.x; i < 256 * kEncReplicas; i += blockDim.x) {
@@ -296,14 +317,49 @@ alias_encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_s
     }
     __syncthreads();
 
-    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t base = smem_addr(s_alias);
-    for (uint32_t chunk = blockIdx.x * kAliasEncWarps + warp; chunk < n_chunks; chunk += gridDim.x * kAliasEncWarps) {
+    const uint32_t tab = base + kAliasEncWarps * kEncWarpSmem, remap = base + kAliasEncFixedSmem, wsm = base + warp * kEncWarpSmem;
+    if (!look) {
+        for (uint32_t chunk = blockIdx.x * kAliasEncWarps + warp; chunk < n_chunks; chunk += gridDim.x * kAliasEncWarps) {
+            const uint64_t first = static_cast<uint64_t>(chunk) * chunk_syms;
+            const uint32_t m = static_cast<uint32_t>(min(static_cast<uint64_t>(chunk_syms), n - first));
+            const uint32_t produced = alias_encode_stream<ALIAS>(in + first, m, tab, remap, wsm, sb,
+                                                                 scratch + static_cast<uint64_t>(chunk + 1) * slot_bytes, status);
+            if (lane == 0) sizes[chunk] = produced;
+        }
+        return;
+    }
+    if (blockIdx.x == 0 && warp == 0) {
+        fused_scanner(look, n_chunks, lane, status);
+        return;
+    }
+    uint8_t* slots = scratch + (static_cast<uint64_t>(blockIdx.x) * kAliasEncWarps + warp) * 2 * slot_bytes;
+    uint32_t pend_chunk = 0, pend_size = 0, parity = 0;
+    bool pending = false;
+    for (;;) {
+        uint32_t chunk = 0;
+        if (lane == 0) chunk = atomicAdd(counter, 1u);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        if (chunk >= n_chunks) break;
         const uint64_t first = static_cast<uint64_t>(chunk) * chunk_syms;
         const uint32_t m = static_cast<uint32_t>(min(static_cast<uint64_t>(chunk_syms), n - first));
-        alias_encode_chunk<ALIAS>(in + first, m, chunk, base + kAliasEncWarps * kEncWarpSmem, base + kAliasEncFixedSmem,
-                           base + warp * kEncWarpSmem, sb, scratch, slot_bytes, sizes, status);
+        const uint32_t produced = alias_encode_stream<ALIAS>(in + first, m, tab, remap, wsm, sb,
+                                                             slots + (parity + 1) * static_cast<uint64_t>(slot_bytes), status);
+        if (lane == 0) st_relaxed_u64(look + chunk, kLookAgg | ((produced + 15u) & ~15u));
+        __syncwarp();
+        if (pending)
+            fused_place(look, pend_chunk, n_chunks, slots + (2 - parity) * static_cast<uint64_t>(slot_bytes), pend_size, blob, blob_cap,
+                        offsets, lane, status);
+        pend_chunk = chunk;
+        pend_size = produced;
+        pending = true;
+        parity ^= 1;
+        __syncwarp();
     }
+    if (pending)
+        fused_place(look, pend_chunk, n_chunks, slots + (2 - parity) * static_cast<uint64_t>(slot_bytes), pend_size, blob, blob_cap,
+                    offsets, lane, status);
 }
 
 inline int alias_sm_count()
@@ -329,21 +385,25 @@ inline void configure_alias_kernels()
     cudaFuncSetAttribute(alias_encode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAliasEncFixedSmem);
 }
 
+// remap == nullptr selects the rans_byte cum2sym coder.  look == nullptr: split mode (sizes[] out, one slot per
+// chunk); otherwise fused mode (two slots per resident warp; look/counter zeroed by the caller).
 inline int launch_alias_encode(cudaStream_t stream, const uint8_t* d_in, uint64_t n, uint32_t chunk_syms, uint32_t n_chunks,
                                uint32_t sb, const AliasEncEntry* enc, const uint16_t* remap, uint8_t* scratch, uint32_t slot,
-                               uint32_t* sizes, uint32_t* status)
+                               uint32_t* sizes, uint64_t* look, uint32_t* counter, uint8_t* blob, uint64_t blob_cap, uint64_t* offsets,
+                               uint32_t* status)
 {
-    uint32_t grid = (n_chunks + kAliasEncWarps - 1) / kAliasEncWarps;
+    uint32_t grid = (n_chunks + (look ? 1 : 0) + kAliasEncWarps - 1) / kAliasEncWarps;
     const uint32_t sms = static_cast<uint32_t>(alias_sm_count());
-    if (grid > sms) grid = sms;                       // persistent: one CTA per SM, chunks strided over CTAs
+    if (grid > sms) grid = sms;                       // persistent: one CTA per SM
     if (remap)
         alias_encode_kernel<true><<<grid, kAliasEncWarps * 32, kAliasEncFixedSmem + (2u << sb), stream>>>(
-            d_in, n, chunk_syms, n_chunks, sb, enc, remap, scratch, slot, sizes, status);
-    else      // rans_byte cum2sym coder: same kernel without the alias remap
+            d_in, n, chunk_syms, n_chunks, sb, enc, remap, scratch, slot, sizes, look, counter, blob, blob_cap, offsets, status);
+    else
         alias_encode_kernel<false><<<grid, kAliasEncWarps * 32, kAliasEncFixedSmem, stream>>>(
-            d_in, n, chunk_syms, n_chunks, sb, enc, nullptr, scratch, slot, sizes, status);
+            d_in, n, chunk_syms, n_chunks, sb, enc, nullptr, scratch, slot, sizes, look, counter, blob, blob_cap, offsets, status);
     return 0;
 }
+inline uint32_t alias_fused_slots() { return static_cast<uint32_t>(alias_sm_count()) * kAliasEncWarps * 2; }
 
 inline int launch_alias_decode(cudaStream_t stream, const uint8_t* blob, uint64_t blob_size, const uint64_t* offsets, uint32_t sb,
                                const AliasDecEntry* dec, uint8_t* out, uint64_t n, uint32_t chunk_syms, uint32_t n_chunks,

@@ -468,9 +468,23 @@ int encode_device(rb200_ctx* ctx, const rb200_model* model, const uint8_t* d_in,
     const size_t n_chunks_sz = rb200_chunk_count(n, chunk_syms);
     if (n_chunks_sz >= (1ull << 31)) return RB200_E_ARG;
     const uint32_t n_chunks = static_cast<uint32_t>(n_chunks_sz);
-    if (n_chunks && model->coder == RB200_CODER_WORD && use_fused_encode(chunk_syms))
+    const bool fused = n_chunks && use_fused_encode(chunk_syms);
+    if (fused && model->coder == RB200_CODER_WORD)
         return encode_word_fused(ctx, model, d_in, n, chunk_syms, n_chunks, d_blob, blob_cap, d_offsets);
     const uint32_t slot = slot_bytes_for(chunk_syms);
+    if (fused && (model->coder == RB200_CODER_ALIAS || model->coder == RB200_CODER_BYTE)) {
+        int rc = reserve(ctx, ctx->scratch, static_cast<size_t>(alias_fused_slots()) * slot + 16);
+        if (rc == RB200_OK) rc = reserve(ctx, ctx->sizes, 16 + static_cast<size_t>(n_chunks) * sizeof(uint64_t));
+        if (rc != RB200_OK) return rc;
+        uint32_t* counter = static_cast<uint32_t*>(ctx->sizes.p);
+        uint64_t* look = reinterpret_cast<uint64_t*>(static_cast<uint8_t*>(ctx->sizes.p) + 16);
+        RB_CUDA(ctx, cudaMemsetAsync(ctx->sizes.p, 0, 16 + static_cast<size_t>(n_chunks) * sizeof(uint64_t), ctx->stream));
+        const bool alias = model->coder == RB200_CODER_ALIAS;
+        launch_alias_encode(ctx->stream, d_in, n, chunk_syms, n_chunks, model->scale_bits, alias ? model->d_alias_enc : model->d_byte_enc,
+                            alias ? model->d_alias_remap : nullptr, static_cast<uint8_t*>(ctx->scratch.p), slot, nullptr, look, counter,
+                            d_blob, blob_cap, d_offsets, ctx->d_status);
+        return check_launch(ctx, alias ? "alias_encode_kernel(fused)" : "byte_encode_kernel(fused)");
+    }
     uint8_t* scratch; uint32_t* sizes; uint64_t* tile_sums;
     int rc = reserve_encode_workspace(ctx, n_chunks, slot, &scratch, &sizes, &tile_sums);
     if (rc != RB200_OK) return rc;
@@ -482,11 +496,11 @@ int encode_device(rb200_ctx* ctx, const rb200_model* model, const uint8_t* d_in,
             rc = check_launch(ctx, "word_encode_kernel");
         } else if (model->coder == RB200_CODER_ALIAS) {
             rc = launch_alias_encode(ctx->stream, d_in, n, chunk_syms, n_chunks, model->scale_bits, model->d_alias_enc,
-                                     model->d_alias_remap, scratch, slot, sizes, ctx->d_status);
+                                     model->d_alias_remap, scratch, slot, sizes, nullptr, nullptr, nullptr, 0, nullptr, ctx->d_status);
             if (rc == RB200_OK) rc = check_launch(ctx, "alias_encode_kernel");
         } else if (model->coder == RB200_CODER_BYTE) {
             rc = launch_alias_encode(ctx->stream, d_in, n, chunk_syms, n_chunks, model->scale_bits, model->d_byte_enc, nullptr, scratch,
-                                     slot, sizes, ctx->d_status);
+                                     slot, sizes, nullptr, nullptr, nullptr, 0, nullptr, ctx->d_status);
             if (rc == RB200_OK) rc = check_launch(ctx, "byte_encode_kernel");
         } else {
             launch_rans64_encode(ctx->stream, d_in, n, chunk_syms, n_chunks, model->scale_bits, model->d_r64_enc, scratch, slot, sizes,

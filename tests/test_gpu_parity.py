@@ -242,14 +242,16 @@ rng = np.random.default_rng(3)
 p = 1.0 / np.arange(1, 257) ** 1.1
 data = rng.choice(256, 3_000_017, p=p / p.sum()).astype(np.uint8)
 orc = oracle.Oracle()
-f, c = orc.model(data, 12)
 ctx = rb.Context(0)
-m = ctx.model(rb.CODER_WORD, 12, f)
-for chunk in (4096, 32, 65536):
-    blob, offs = ctx.encode_host(m, data, chunk)
-    ob, oo = orc.chunked_encode(oracle.CODER_WORD, data, f, c, chunk)
-    assert np.array_equal(offs, oo) and np.array_equal(blob, ob), chunk
-    assert np.array_equal(ctx.decode_host(m, blob, offs, data.size, chunk), data)
+for coder, sb in ((rb.CODER_WORD, 12), (rb.CODER_ALIAS, 16), (rb.CODER_BYTE, 14)):
+    f, c = orc.model(data, sb)
+    m = ctx.model(coder, sb, f)
+    for chunk in (4096, 32, 65536):
+        blob, offs = ctx.encode_host(m, data, chunk)
+        ob, oo = orc.chunked_encode(coder, data, f, c, chunk, scale_bits=sb)
+        assert np.array_equal(offs, oo) and np.array_equal(blob, ob), (coder, chunk)
+        assert np.array_equal(ctx.decode_host(m, blob, offs, data.size, chunk), data)
+    m.close()
 print("fused ok", ctx.launches)
 ''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, RB200_ENCODE_PATH=path)
