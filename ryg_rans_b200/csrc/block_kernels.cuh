@@ -80,7 +80,8 @@ __global__ void __launch_bounds__(kModelWarps * 32)
 block_model_kernel(const uint8_t* __restrict__ in, uint32_t block_size, uint16_t* __restrict__ block_freqs,
                    uint32_t* __restrict__ status)
 {
-    __shared__ uint32_t s_h[kModelWarps][256];
+    // one private histogram per warp (more copies per warp were measured slower: the copies share banks)
+    __shared__ __align__(16) uint32_t s_h[kModelWarps][256];
     __shared__ uint32_t s_cnt[256];
     __shared__ uint32_t s_cum[257];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -135,36 +136,40 @@ block_model_kernel(const uint8_t* __restrict__ in, uint32_t block_size, uint16_t
     if (lane == 31) s_cum[256] = kWordSlots;                        // 4096 * total / total
     __syncwarp();
 
-    // main.cpp:90-116, symbols in order; the arg-min over 256 widths is done by the warp
+    // main.cpp:90-116, symbols in order.  Moving the boundaries between donor and taker by one changes exactly
+    // two widths (donor - 1, taker + 1), so the loop runs on widths; the arg-min over 256 widths is warp-wide
+    // with the key (width << 8 | symbol): lowest width first, lowest symbol on ties, as the reference's scan.
+    uint32_t* s_w = s_h[0];                                         // reuse: 256 widths
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const uint32_t t = 8 * lane + j;
+        s_w[t] = s_cum[t + 1] - s_cum[t];
+    }
+    __syncwarp();
     bool failed = false;
     for (uint32_t s = 0; s < 256; s++) {
-        if (s_cnt[s] == 0 || s_cum[s + 1] != s_cum[s]) continue;    // warp-uniform
-        uint32_t key = 0xffffffffu;                                 // (width << 8 | symbol): lowest width, then lowest symbol
+        if (s_cnt[s] == 0 || s_w[s] != 0) continue;                 // warp-uniform
+        uint32_t key = 0xffffffffu;
+        const uint4 lo = *reinterpret_cast<const uint4*>(&s_w[8 * lane]);
+        const uint4 hi = *reinterpret_cast<const uint4*>(&s_w[8 * lane + 4]);
+        const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const uint32_t t = 8 * lane + j;
-            const uint32_t w = s_cum[t + 1] - s_cum[t];
-            if (w > 1) key = min(key, (w << 8) | t);
-        }
+        for (int j = 0; j < 8; j++)
+            if (w[j] > 1) key = min(key, (w[j] << 8) | (8 * lane + j));
         key = __reduce_min_sync(0xffffffffu, key);
         if (key == 0xffffffffu) { failed = true; break; }           // main.cpp:104
-        const uint32_t donor = key & 0xffu;
         __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const uint32_t t = 8 * lane + j;
-            if (donor < s) { if (t > donor && t <= s) s_cum[t] -= 1; }   // main.cpp:107-109
-            else           { if (t > s && t <= donor) s_cum[t] += 1; }   // main.cpp:110-113
+        if (lane == 0) {
+            s_w[key & 0xffu] -= 1;                                  // main.cpp:107-113 in terms of widths
+            s_w[s] += 1;
         }
         __syncwarp();
     }
     if (failed && lane == 0) atomicOr(status, kStatStream);
     uint16_t* dst = block_freqs + static_cast<uint64_t>(blockIdx.x) * 256;
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-        const uint32_t t = 8 * lane + j;
-        dst[t] = static_cast<uint16_t>(s_cum[t + 1] - s_cum[t]);    // main.cpp:127
-    }
+    for (int j = 0; j < 8; j++) dst[8 * lane + j] = static_cast<uint16_t>(s_w[8 * lane + j]);     // main.cpp:127
 }
 
 inline void launch_block_models(cudaStream_t stream, const uint8_t* d_in, uint32_t n_blocks, uint32_t block_size,
