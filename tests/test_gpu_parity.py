@@ -388,3 +388,27 @@ def test_large_chunks_use_bounded_scratch(gpu_ctx, oracle_lib, gen):
     data = gen("zipf", (1 << 20) + 77, 5)
     for coder, sb in ((WORD, 12), (ALIAS, 16)):
         _roundtrip(gpu_ctx, oracle_lib, data, coder, sb, 1 << 18)
+
+
+def test_shards_concatenate_on_one_gpu(gpu_ctx, oracle_lib, gen):
+    """SURVEY 8(e) degraded to one GPU: encode N shards one after the other (what N ranks would do), concatenate
+    blobs and directories the way ryg_rans_b200.shard.gather_blobs does, and decode the whole thing in one call."""
+    from ryg_rans_b200.shard import shard_bounds
+    n, chunk, world = 1_000_003, 4096, 4
+    data = gen("text", n, 41)
+    freqs, cum = _model(oracle_lib, data, 12)
+    model = gpu_ctx.model(WORD, 12, freqs)
+    blobs, dirs, base = [], [], 0
+    for r in range(world):
+        lo, hi = shard_bounds(n, world, r, chunk)
+        b, o = gpu_ctx.encode_host(model, data[lo:hi], chunk)
+        assert b.size % 16 == 0
+        blobs.append(b)
+        dirs.append(o[:-1] + np.uint64(base))
+        base += b.size
+    blob = np.concatenate(blobs)
+    offs = np.concatenate(dirs + [np.array([base], np.uint64)])
+    whole, woffs = gpu_ctx.encode_host(model, data, chunk)
+    assert np.array_equal(blob, whole) and np.array_equal(offs, woffs)
+    assert np.array_equal(gpu_ctx.decode_host(model, blob, offs, n, chunk), data)
+    model.close()
