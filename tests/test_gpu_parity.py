@@ -373,8 +373,9 @@ def test_cpp_driver_exam_gpu(coder):
     import os
     import subprocess
     import ryg_rans_b200 as rb
-    rb.build()
     exe = os.path.join(os.path.dirname(rb.LIB_PATH), "exam_gpu")
+    if not os.path.exists(exe):
+        rb.build()
     assert os.path.exists(exe)
     out = subprocess.run([exe, "-", coder, "8192", str(8 << 20)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr
