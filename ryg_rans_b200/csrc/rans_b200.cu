@@ -49,6 +49,8 @@ struct rb200_ctx {
     cudaEvent_t ev_in[kMaxSlices] = {}, ev_done[kMaxSlices] = {};
     cudaEvent_t ev_start = nullptr, ev_out = nullptr;
     uint64_t* h_slice_total = nullptr;   // pinned, kMaxSlices entries
+    uint64_t* h_dir = nullptr;           // pinned staging for directories (caller's `offsets` may be pageable)
+    size_t h_dir_cap = 0;                // entries
 };
 
 struct rb200_model {
@@ -224,6 +226,7 @@ extern "C" void rb200_ctx_destroy(rb200_ctx* ctx)
     if (ctx->d_status) cudaFree(ctx->d_status);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
     if (ctx->h_slice_total) cudaFreeHost(ctx->h_slice_total);
+    if (ctx->h_dir) cudaFreeHost(ctx->h_dir);
     for (int i = 0; i < rb200_ctx::kMaxSlices; i++) {
         if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
         if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
@@ -443,13 +446,18 @@ int sm_count(int device)
     return sms;
 }
 
+uint32_t fused_word_grid(rb200_ctx* ctx, uint32_t n_chunks)
+{
+    const uint32_t want = (n_chunks + 1 + kEncWarps - 1) / kEncWarps;       // + 1: one warp of the grid is the scanner
+    const uint32_t grid = static_cast<uint32_t>(sm_count(ctx->device)) * RB200_ENC_MINBLOCKS;
+    return grid > want ? want : grid;
+}
+
 int encode_word_fused(rb200_ctx* ctx, const rb200_model* model, const uint8_t* d_in, size_t n, uint32_t chunk_syms, uint32_t n_chunks,
                       uint8_t* d_blob, size_t blob_cap, uint64_t* d_offsets)
 {
     const uint32_t slot = slot_bytes_for(chunk_syms);
-    const uint32_t want = (n_chunks + 1 + kEncWarps - 1) / kEncWarps;       // + 1: one warp of the grid is the scanner
-    uint32_t grid = static_cast<uint32_t>(sm_count(ctx->device)) * RB200_ENC_MINBLOCKS;
-    if (grid > want) grid = want;
+    const uint32_t grid = fused_word_grid(ctx, n_chunks);
     int rc = reserve(ctx, ctx->scratch, static_cast<size_t>(grid) * kEncWarps * 2 * slot + 16);  // two slots per resident warp
     if (rc == RB200_OK) rc = reserve(ctx, ctx->sizes, 16 + static_cast<size_t>(n_chunks) * sizeof(uint64_t));
     if (rc != RB200_OK) return rc;
@@ -460,6 +468,23 @@ int encode_word_fused(rb200_ctx* ctx, const rb200_model* model, const uint8_t* d
         d_in, n, chunk_syms, n_chunks, model->d_word_enc, static_cast<uint8_t*>(ctx->scratch.p), slot, look, counter, d_blob, blob_cap,
         d_offsets, ctx->d_status);
     return check_launch(ctx, "word_encode_fused_kernel");
+}
+
+// Grows the encode workspaces to what a call over `n_chunks` chunks needs (the host pipeline does this once
+// for its largest slice so that no slice has to stall on a reallocation).
+int reserve_encode(rb200_ctx* ctx, const rb200_model* model, uint32_t n_chunks, uint32_t chunk_syms)
+{
+    if (!n_chunks) return RB200_OK;
+    const uint32_t slot = slot_bytes_for(chunk_syms);
+    if (use_fused_encode(chunk_syms) && model->coder != RB200_CODER_RANS64) {
+        const size_t slots = model->coder == RB200_CODER_WORD ? static_cast<size_t>(fused_word_grid(ctx, n_chunks)) * kEncWarps * 2
+                                                              : static_cast<size_t>(alias_fused_slots());
+        int rc = reserve(ctx, ctx->scratch, slots * slot + 16);
+        if (rc == RB200_OK) rc = reserve(ctx, ctx->sizes, 16 + static_cast<size_t>(n_chunks) * sizeof(uint64_t));
+        return rc;
+    }
+    uint8_t* scratch; uint32_t* sizes; uint64_t* tile_sums;
+    return reserve_encode_workspace(ctx, n_chunks, slot, &scratch, &sizes, &tile_sums);
 }
 
 int encode_device(rb200_ctx* ctx, const rb200_model* model, const uint8_t* d_in, size_t n, uint32_t chunk_syms,
@@ -551,19 +576,72 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 
 namespace {
 
-// symbols per pipeline slice: big enough that PCIe time dwarfs launch overhead, small enough to overlap
-size_t slice_symbols(size_t n, uint32_t chunk_syms)
+int reserve_dir(rb200_ctx* ctx, size_t entries)
 {
-    size_t target = 32u << 20;
-    if (n / target >= static_cast<size_t>(rb200_ctx::kMaxSlices)) target = n / (rb200_ctx::kMaxSlices - 1);
-    size_t chunks = (target + chunk_syms - 1) / chunk_syms;
-    if (chunks == 0) chunks = 1;
-    return chunks * static_cast<size_t>(chunk_syms);
+    if (entries <= ctx->h_dir_cap) return RB200_OK;
+    if (ctx->h_dir) {
+        RB_CUDA(ctx, cudaStreamSynchronize(ctx->s_in));
+        RB_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
+        RB_CUDA(ctx, cudaFreeHost(ctx->h_dir));
+        ctx->h_dir = nullptr;
+        ctx->h_dir_cap = 0;
+    }
+    const size_t want = entries + entries / 8 + 64;
+    cudaError_t e = cudaMallocHost(&ctx->h_dir, want * sizeof(uint64_t));
+    if (e != cudaSuccess) {
+        ctx->h_dir = nullptr;
+        cuda_fail(ctx, e, "cudaMallocHost(directory staging)");
+        return RB200_E_NOMEM;
+    }
+    ctx->h_dir_cap = want;
+    return RB200_OK;
+}
+
+// One pipeline slice of a host-mode call: chunks [c0, c0 + cnt) = symbols [lo, lo + len).
+struct Slice {
+    size_t c0, cnt, lo, len;
+};
+
+// Slice plan for the host pipeline.  Steady-state slices are `RB200_SLICE_MIB` (default 32 MiB) of symbols:
+// big enough that PCIe time dwarfs launch overhead and the per-slice host wake-up, small enough to overlap.
+// The first and last three slices ramp (1/8, 1/4, 1/2 of that) so that the pipeline fill (first H2D) and
+// drain (last D2H), which nothing overlaps, are short.  Returns the number of slices (<= kMaxSlices).
+size_t plan_slices(size_t n, uint32_t chunk_syms, Slice* out)
+{
+    static const size_t tuned = [] {        // tuning knob for the host pipeline (1..1024 MiB)
+        const char* e = std::getenv("RB200_SLICE_MIB");
+        const long v = e ? std::atol(e) : 0;
+        return (v >= 1 && v <= 1024) ? static_cast<size_t>(v) << 20 : static_cast<size_t>(32u << 20);
+    }();
+    const size_t total = rb200_chunk_count(n, chunk_syms);
+    size_t tc = (tuned + chunk_syms - 1) / chunk_syms;                // chunks per steady-state slice
+    if (tc == 0) tc = 1;
+    const size_t room = rb200_ctx::kMaxSlices - 8;
+    if (total / tc >= room) tc = total / room + 1;
+    size_t ramp[3] = {tc / 8, tc / 4, tc / 2};
+    const bool ramped = total >= 4 * tc && ramp[0] > 0;
+    size_t k = 0, c = 0;
+    auto push = [&](size_t cnt) {
+        if (cnt == 0) return;
+        if (cnt > total - c) cnt = total - c;
+        const size_t lo = c * chunk_syms;
+        const size_t len = (n - lo < cnt * chunk_syms) ? n - lo : cnt * chunk_syms;
+        out[k++] = Slice{c, cnt, lo, len};
+        c += cnt;
+    };
+    const size_t tail = ramped ? ramp[0] + ramp[1] + ramp[2] : 0;
+    if (ramped)
+        for (int r = 0; r < 3; r++) push(ramp[r]);
+    while (total - c > tail) push((total - c - tail < tc) ? total - c - tail : tc);
+    if (ramped)
+        for (int r = 2; r >= 0; r--) push(ramp[r]);
+    return k;
 }
 
 // Host buffers -> blob, overlapped: slice i+1 is copied in while slice i is encoded and slice i-1 is
 // copied out.  Every slice is its own container in a staging region; because containers end 16-byte
-// aligned they concatenate, and the directory entries only need the running base added.
+// aligned they concatenate, and the directory entries only need the running base added.  Directories are
+// staged in pinned memory (an async copy to a pageable `offsets` would block the issuing thread).
 int encode_host(rb200_ctx* ctx, const rb200_model* model, const uint8_t* in, size_t n, uint32_t chunk_syms, uint8_t* blob,
                 size_t blob_cap, uint64_t* offsets, size_t* blob_size)
 {
@@ -573,32 +651,35 @@ int encode_host(rb200_ctx* ctx, const rb200_model* model, const uint8_t* in, siz
         if (blob_size) *blob_size = 0;
         return RB200_OK;
     }
-    const size_t slice = slice_symbols(n, chunk_syms);
-    const size_t n_slices = (n + slice - 1) / slice;
-    const size_t chunks_per_slice = slice / chunk_syms;
-    const size_t slice_bound = rb200_encode_bound(slice, chunk_syms);
+    Slice sl[rb200_ctx::kMaxSlices];
+    const size_t n_slices = plan_slices(n, chunk_syms, sl);
+    size_t max_cnt = 0;
+    for (size_t i = 0; i < n_slices; i++) max_cnt = sl[i].cnt > max_cnt ? sl[i].cnt : max_cnt;
+    // slice i's container is built at bound(symbols before it); its directory at c0 + i (cnt + 1 entries)
     int rc = reserve(ctx, ctx->st_in, n + 16);
-    if (rc == RB200_OK) rc = reserve(ctx, ctx->st_blob, n_slices * slice_bound + 16);
-    if (rc == RB200_OK) rc = reserve(ctx, ctx->st_offsets, n_slices * (chunks_per_slice + 1) * sizeof(uint64_t));
+    if (rc == RB200_OK) rc = reserve(ctx, ctx->st_blob, n_chunks * static_cast<size_t>(slot_bytes_for(chunk_syms)) + 16);
+    if (rc == RB200_OK) rc = reserve(ctx, ctx->st_offsets, (n_chunks + n_slices) * sizeof(uint64_t));
+    if (rc == RB200_OK) rc = reserve_dir(ctx, n_chunks + n_slices);
+    if (rc == RB200_OK) rc = reserve_encode(ctx, model, static_cast<uint32_t>(max_cnt), chunk_syms);   // no regrowth mid-pipeline
     if (rc != RB200_OK) return rc;
     uint8_t* d_in = static_cast<uint8_t*>(ctx->st_in.p);
     uint8_t* d_blob = static_cast<uint8_t*>(ctx->st_blob.p);
     uint64_t* d_off = static_cast<uint64_t*>(ctx->st_offsets.p);
+    const size_t slot = slot_bytes_for(chunk_syms);
 
     RB_CUDA(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));       // staging buffers may still be in use upstream
     RB_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_start, 0));
     RB_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_start, 0));
 
     auto issue = [&](size_t i) -> int {      // H2D + kernels for slice i
-        const size_t lo = i * slice, len = (n - lo < slice) ? n - lo : slice;
-        RB_CUDA(ctx, cudaMemcpyAsync(d_in + lo, in + lo, len, cudaMemcpyHostToDevice, ctx->s_in));
+        const Slice& s = sl[i];
+        RB_CUDA(ctx, cudaMemcpyAsync(d_in + s.lo, in + s.lo, s.len, cudaMemcpyHostToDevice, ctx->s_in));
         RB_CUDA(ctx, cudaEventRecord(ctx->ev_in[i], ctx->s_in));
         RB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[i], 0));
-        uint64_t* so = d_off + i * (chunks_per_slice + 1);
-        int r = encode_device(ctx, model, d_in + lo, len, chunk_syms, d_blob + i * slice_bound, slice_bound, so);
+        uint64_t* so = d_off + s.c0 + i;
+        int r = encode_device(ctx, model, d_in + s.lo, s.len, chunk_syms, d_blob + s.c0 * slot, s.cnt * slot, so);
         if (r != RB200_OK) return r;
-        const size_t cnt = rb200_chunk_count(len, chunk_syms);
-        RB_CUDA(ctx, cudaMemcpyAsync(&ctx->h_slice_total[i], so + cnt, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        RB_CUDA(ctx, cudaMemcpyAsync(&ctx->h_slice_total[i], so + s.cnt, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
         RB_CUDA(ctx, cudaEventRecord(ctx->ev_done[i], ctx->stream));
         return RB200_OK;
     };
@@ -614,15 +695,14 @@ int encode_host(rb200_ctx* ctx, const rb200_model* model, const uint8_t* in, siz
         }
         RB_CUDA(ctx, cudaEventSynchronize(ctx->ev_done[i]));          // slice i's size is now on the host
         const size_t total = static_cast<size_t>(ctx->h_slice_total[i]);
-        const size_t lo = i * slice, len = (n - lo < slice) ? n - lo : slice;
-        const size_t cnt = rb200_chunk_count(len, chunk_syms), c0 = i * chunks_per_slice;
+        const Slice& s = sl[i];
         if (base + total > blob_cap) {
             overflow = true;
         } else if (!overflow) {
             RB_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_done[i], 0));
-            RB_CUDA(ctx, cudaMemcpyAsync(blob + base, d_blob + i * slice_bound, total, cudaMemcpyDeviceToHost, ctx->s_out));
-            RB_CUDA(ctx, cudaMemcpyAsync(offsets + c0, d_off + i * (chunks_per_slice + 1), cnt * sizeof(uint64_t),
-                                         cudaMemcpyDeviceToHost, ctx->s_out));
+            RB_CUDA(ctx, cudaMemcpyAsync(blob + base, d_blob + s.c0 * slot, total, cudaMemcpyDeviceToHost, ctx->s_out));
+            RB_CUDA(ctx, cudaMemcpyAsync(ctx->h_dir + s.c0 + i, d_off + s.c0 + i, s.cnt * sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                                         ctx->s_out));
         }
         ctx->h_slice_total[i] = base;                                 // reuse as "base of slice i"
         base += total;
@@ -632,11 +712,11 @@ int encode_host(rb200_ctx* ctx, const rb200_model* model, const uint8_t* in, siz
     rc = rb200_sync(ctx);
     if (rc != RB200_OK) return rc;
     if (overflow) return RB200_E_SPACE;
-    for (size_t i = 1; i < n_slices; i++) {                           // rebase the directory
+    for (size_t i = 0; i < n_slices; i++) {                           // rebase the directory into the caller's array
         const uint64_t add = ctx->h_slice_total[i];
-        const size_t c0 = i * chunks_per_slice;
-        const size_t c1 = (c0 + chunks_per_slice < n_chunks) ? c0 + chunks_per_slice : n_chunks;
-        for (size_t c = c0; c < c1; c++) offsets[c] += add;
+        const uint64_t* src = ctx->h_dir + sl[i].c0 + i;
+        uint64_t* dst = offsets + sl[i].c0;
+        for (size_t c = 0; c < sl[i].cnt; c++) dst[c] = src[c] + add;
     }
     offsets[n_chunks] = base;
     if (blob_size) *blob_size = base;
@@ -651,14 +731,12 @@ int decode_host(rb200_ctx* ctx, const rb200_model* model, const uint8_t* blob, s
     const size_t n_chunks = rb200_chunk_count(n, chunk_syms);
     if (n == 0) return RB200_OK;
     if (offsets[n_chunks] != blob_size) return RB200_E_STREAM;
-    for (size_t c = 0; c < n_chunks; c++)                            // the copies below trust these
-        if (offsets[c] > offsets[c + 1] || offsets[c + 1] > blob_size) return RB200_E_STREAM;
-    const size_t slice = slice_symbols(n, chunk_syms);
-    const size_t n_slices = (n + slice - 1) / slice;
-    const size_t chunks_per_slice = slice / chunk_syms;
+    Slice sl[rb200_ctx::kMaxSlices];
+    const size_t n_slices = plan_slices(n, chunk_syms, sl);
     int rc = reserve(ctx, ctx->st_blob, blob_size + 16);
     if (rc == RB200_OK) rc = reserve(ctx, ctx->st_offsets, (n_chunks + 1) * sizeof(uint64_t));
     if (rc == RB200_OK) rc = reserve(ctx, ctx->st_out, n + 16);
+    if (rc == RB200_OK) rc = reserve_dir(ctx, n_chunks + 1);
     if (rc != RB200_OK) return rc;
     uint8_t* d_blob = static_cast<uint8_t*>(ctx->st_blob.p);
     uint64_t* d_off = static_cast<uint64_t*>(ctx->st_offsets.p);
@@ -667,22 +745,26 @@ int decode_host(rb200_ctx* ctx, const rb200_model* model, const uint8_t* blob, s
     RB_CUDA(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
     RB_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_start, 0));
     RB_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_start, 0));
-    RB_CUDA(ctx, cudaMemcpyAsync(d_off, offsets, (n_chunks + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->s_in));
+    for (size_t c = 0; c < n_chunks; c++) {                          // the copies below trust these
+        if (offsets[c] > offsets[c + 1] || offsets[c + 1] > blob_size) return RB200_E_STREAM;
+        ctx->h_dir[c] = offsets[c];
+    }
+    ctx->h_dir[n_chunks] = offsets[n_chunks];
+    RB_CUDA(ctx, cudaMemcpyAsync(d_off, ctx->h_dir, (n_chunks + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->s_in));
     for (size_t i = 0; i < n_slices; i++) {
-        const size_t c0 = i * chunks_per_slice;
-        const size_t c1 = (c0 + chunks_per_slice < n_chunks) ? c0 + chunks_per_slice : n_chunks;
-        const size_t lo = i * slice, len = (n - lo < slice) ? n - lo : slice;
+        const Slice& s = sl[i];
+        const size_t c1 = s.c0 + s.cnt;
         // bytes of chunks [c0, c1): from the (aligned) end of chunk c0-1 to the end of chunk c1-1
-        const size_t b0 = c0 ? static_cast<size_t>(offsets[c0] & ~15ull) : 0;
+        const size_t b0 = s.c0 ? static_cast<size_t>(offsets[s.c0] & ~15ull) : 0;
         const size_t b1 = static_cast<size_t>(offsets[c1] & ~15ull);
         if (b1 > b0) RB_CUDA(ctx, cudaMemcpyAsync(d_blob + b0, blob + b0, b1 - b0, cudaMemcpyHostToDevice, ctx->s_in));
         RB_CUDA(ctx, cudaEventRecord(ctx->ev_in[i], ctx->s_in));
         RB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[i], 0));
-        rc = decode_device(ctx, model, d_blob, blob_size, d_off + c0, chunk_syms, d_out + lo, len);
+        rc = decode_device(ctx, model, d_blob, blob_size, d_off + s.c0, chunk_syms, d_out + s.lo, s.len);
         if (rc != RB200_OK) return rc;
         RB_CUDA(ctx, cudaEventRecord(ctx->ev_done[i], ctx->stream));
         RB_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_done[i], 0));
-        RB_CUDA(ctx, cudaMemcpyAsync(out + lo, d_out + lo, len, cudaMemcpyDeviceToHost, ctx->s_out));
+        RB_CUDA(ctx, cudaMemcpyAsync(out + s.lo, d_out + s.lo, s.len, cudaMemcpyDeviceToHost, ctx->s_out));
     }
     RB_CUDA(ctx, cudaEventRecord(ctx->ev_out, ctx->s_out));
     RB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_out, 0));

@@ -260,15 +260,16 @@ print("fused ok", ctx.launches)
 
 
 def test_host_pipeline_many_slices(gpu_ctx, oracle_lib, gen):
-    """Host-mode calls are a slice pipeline (32 MiB slices on three streams); cross several slice boundaries."""
-    n = (32 << 20) * 3 + 12345
+    """Host-mode calls are a slice pipeline (32 MiB slices on three streams, ramped at both ends: 4, 8, 16,
+    32, 32, 16, 8, 4 MiB here); cross several slice boundaries."""
+    n = (32 << 20) * 4 + 12345
     data = gen("text", n, 77)
     freqs, cum = _model(oracle_lib, data, 12)
     model = gpu_ctx.model(WORD, 12, freqs)
     blob, offs = gpu_ctx.encode_host(model, data, 8192)
     assert blob.size % 16 == 0 and offs[-1] == blob.size
     # slices are independent containers that were concatenated: check a chunk on each side of a slice boundary
-    for c in (0, 4095, 4096, 8191, 8192, len(offs) - 2):
+    for c in (0, 511, 512, 1535, 1536, 3583, 3584, 7679, 7680, 11775, 11776, 13823, 13824, len(offs) - 2):
         lo = c * 8192
         s = oracle_lib.encode(orc.CODER_WORD, data[lo:lo + 8192], freqs, cum, 32)
         end = int(offs[c + 1]) & ~15
@@ -276,6 +277,41 @@ def test_host_pipeline_many_slices(gpu_ctx, oracle_lib, gen):
     out = gpu_ctx.decode_host(model, blob, offs, n, 8192)
     assert np.array_equal(out, data)
     model.close()
+
+
+def test_host_pipeline_ramped_slices():
+    """The host pipeline ramps its first and last three slices (1/8, 1/4, 1/2 of RB200_SLICE_MIB).  With 1 MiB
+    slices a 9 MB input takes the ramped plan; the container must not depend on the slicing: equal to the
+    oracle's for every coder, also with tiny and ragged chunks and a non-pinned directory."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r)
+import oracle, ryg_rans_b200 as rb
+rng = np.random.default_rng(5)
+p = 1.0 / np.arange(1, 257) ** 1.1
+data = rng.choice(256, 9_000_017, p=p / p.sum()).astype(np.uint8)
+orc = oracle.Oracle()
+ctx = rb.Context(0)
+for coder, sb, chunks in ((rb.CODER_WORD, 12, (8192, 1000, 32)), (rb.CODER_ALIAS, 16, (8192,)), (rb.CODER_BYTE, 14, (4096,)),
+                          (rb.CODER_RANS64, 14, (8192,))):
+    f, c = orc.model(data, sb)
+    m = ctx.model(coder, sb, f)
+    for chunk in chunks:
+        blob, offs = ctx.encode_host(m, data, chunk)
+        ob, oo = orc.chunked_encode(coder, data, f, c, chunk, scale_bits=sb)
+        assert np.array_equal(offs, oo) and np.array_equal(blob, ob), (coder, chunk)
+        assert np.array_equal(ctx.decode_host(m, blob, offs, data.size, chunk), data)
+    m.close()
+print("ramped ok", ctx.launches)
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RB200_SLICE_MIB="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ramped ok" in out.stdout, out.stderr[-2000:]
+    # 9 MB / 1 MiB slices with ramps = 6 ramp + 7 steady slices per call; far more launches than one per call
+    assert int(out.stdout.split()[-1]) > 100
 
 
 @pytest.mark.parametrize("coder,sb,kind", [(WORD, 12, "uniform"), (ALIAS, 16, "zipf")])
