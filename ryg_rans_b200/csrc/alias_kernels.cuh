@@ -203,9 +203,9 @@ __device__ __forceinline__ void alias_enc_step(AliasEncState& st, uint32_t sym, 
     st.wpos -= __popc(m1) + __popc(m2);
     if (active) {
         if (ALIAS) {
-            const uint32_t hi = __umulhi(st.x, e.x);                               // exact x / freq, as in the word encoder
-            const uint32_t lo = st.x + hi;
-            const uint32_t q = funnel_shr_wrap(lo, lo < hi ? 1u : 0u, e.w);
+            // exact x / freq with the 33-bit round-up reciprocal 2^32 + magic, as in the word encoder; here
+            // x < 2^31 (rans_byte.h:26-28), so x + mulhi(x, magic) < 2^32 and there is no carry to fold in
+            const uint32_t q = funnel_shr_wrap(st.x + __umulhi(st.x, e.x), 0u, e.w);
             const uint32_t r = st.x - q * e.y;                                     // x % freq
             st.x = (q << sb) + lds_u16_ro(remap + 2u * (r + e.z));                 // main_alias.cpp:249
         } else {

@@ -271,17 +271,37 @@ block_encode_kernel(const uint8_t* __restrict__ in, uint32_t block_size, const u
     const uint16_t* freqs = block_freqs + static_cast<uint64_t>(blockIdx.x) * 256;
     const uint32_t per_block = block_size / chunk_syms;
     const bool ok = block_prefix(freqs, s_cum, &s_flag[0]);
+    // 32-bit reciprocal where it is exact for every symbol of this block's model (tables.h: enc32), else the 33-bit one
+    bool exact32 = true;
+    for (uint32_t s = tid; s < 256; s += blockDim.x) {
+        const uint32_t f = ok ? s_cum[s + 1] - s_cum[s] : 0;
+        if (f > 1) {
+            uint32_t sh = 0;
+            while ((1u << sh) < f) sh++;
+            const uint64_t pow = 1ull << (31 + sh), M32 = (pow + f - 1) / f;
+            if (M32 >> 32 || ((static_cast<uint64_t>(f) << 20) - 1) * (M32 * f - pow) >= pow) exact32 = false;
+        }
+    }
+    const bool r32 = __syncthreads_and(exact32) != 0;
     for (uint32_t s = tid; s < 256; s += blockDim.x) {
         const uint32_t f = ok ? s_cum[s + 1] - s_cum[s] : 0;
         WordEncEntry e = {0u, kEncBadSymbol};
         if (f) {
             uint32_t sh = 0;
             while ((1u << sh) < f) sh++;
-            const uint64_t M = ((1ull << (32 + sh)) + f - 1) / f;          // in [2^32, 2^33): keep the low word
-            e.magic = static_cast<uint32_t>(M);
-            e.packed = f | (s_cum[s] << 13) | (sh << 25);
+            if (!r32) {
+                const uint64_t M = ((1ull << (32 + sh)) + f - 1) / f;      // in [2^32, 2^33): keep the low word
+                e.magic = static_cast<uint32_t>(M);
+                e.packed = f | (s_cum[s] << 13) | (sh << 25);
+            } else if (f == 1) {
+                e.magic = 0xffffffffu;
+                e.packed = f | (s_cum[s] << 13);
+            } else {
+                e.magic = static_cast<uint32_t>(((1ull << (31 + sh)) + f - 1) / f);
+                e.packed = f | (s_cum[s] << 13) | ((sh - 1) << 25);
+            }
         }
-        const uint4 x = word_enc_expand(e);
+        const uint4 x = r32 ? word_enc_expand<true>(e) : word_enc_expand<false>(e);
 #pragma unroll
         for (uint32_t r = 0; r < kEncReplicas; r++) s_tab[s * kEncReplicas + r] = x;
     }
@@ -289,8 +309,11 @@ block_encode_kernel(const uint8_t* __restrict__ in, uint32_t block_size, const u
     if (warp >= per_block) return;
     const uint32_t chunk = blockIdx.x * per_block + warp;
     const uint8_t* src = in + static_cast<uint64_t>(blockIdx.x) * block_size + static_cast<uint64_t>(warp) * chunk_syms;
-    word_encode_chunk(src, chunk_syms, chunk, smem_addr(s_enc), smem_addr(s_enc) + kEncTableBytes + warp * kEncWarpSmem, scratch,
-                      slot_bytes, sizes, status);
+    const uint32_t wsm = smem_addr(s_enc) + kEncTableBytes + warp * kEncWarpSmem;
+    if (r32)
+        word_encode_chunk<true>(src, chunk_syms, chunk, smem_addr(s_enc), wsm, scratch, slot_bytes, sizes, status);
+    else
+        word_encode_chunk<false>(src, chunk_syms, chunk, smem_addr(s_enc), wsm, scratch, slot_bytes, sizes, status);
 }
 
 inline uint32_t block_threads(uint32_t block_size, uint32_t chunk_syms)

@@ -167,6 +167,7 @@ int build_word_device_tables(const uint32_t freqs[256], WordDeviceTables& t)
     }
     if (cum[256] != 4096) return RB200_E_MODEL;
     t.wide = 0;
+    t.enc32_ok = 1;
     for (int s = 0; s < 256; s++) {
         const uint32_t f = freqs[s];
         if (f == 4096) t.wide = 1;
@@ -176,12 +177,25 @@ int build_word_device_tables(const uint32_t freqs[256], WordDeviceTables& t)
         //   M = ceil(2^(32+sh) / f) = 2^32 + magic,  q = (x + mulhi(x, magic)) >> sh
         if (f == 0) {
             t.enc[s] = {0u, kEncBadSymbol};
+            t.enc32[s] = {0u, kEncBadSymbol};
         } else {
             const uint32_t sh = ceil_log2(f);
             const unsigned __int128 one = 1;
             const unsigned __int128 M = ((one << (32 + sh)) + f - 1) / f;
             const uint32_t magic = static_cast<uint32_t>(M - (one << 32));
             t.enc[s] = {magic, f | (cum[s] << 13) | (sh << 25)};
+            // 32-bit reciprocal, exact on x < f << 20 (see tables.h)
+            if (f == 1) {
+                t.enc32[s] = {0xffffffffu, f | (cum[s] << 13)};
+            } else {
+                const uint32_t s32 = sh - 1;
+                const uint64_t pow = 1ull << (32 + s32);
+                const uint64_t M32 = (pow + f - 1) / f;                    // < 2^32 because 2^s32 < f
+                const uint64_t err = M32 * f - pow;                        // < f
+                const uint64_t xmax = (static_cast<uint64_t>(f) << 20) - 1;
+                if (M32 >> 32 || xmax * err >= pow) t.enc32_ok = 0;
+                t.enc32[s] = {static_cast<uint32_t>(M32), f | (cum[s] << 13) | (s32 << 25)};
+            }
         }
     }
     return RB200_OK;

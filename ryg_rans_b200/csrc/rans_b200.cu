@@ -59,7 +59,8 @@ struct rb200_model {
     uint32_t scale_bits = 0;
     int wide = 0;
     uint32_t* d_word_dec = nullptr;          // 4096 x u32
-    WordEncEntry* d_word_enc = nullptr;      // 256
+    WordEncEntry* d_word_enc = nullptr;      // 256; the 32-bit-reciprocal table when enc_r32 (tables.h)
+    int enc_r32 = 0;
     AliasDecEntry* d_alias_dec = nullptr;    // 256 x 16 B
     AliasEncEntry* d_alias_enc = nullptr;    // 256
     uint16_t* d_alias_remap = nullptr;       // 1 << scale_bits
@@ -204,10 +205,14 @@ extern "C" int rb200_ctx_create(rb200_ctx** out, int device, void* stream)
     // the decoders want the large shared-memory carve-out (tables + per-warp rings)
     cudaFuncSetAttribute(word_decode_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(word_decode_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(word_encode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(word_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmemBytes);
-    cudaFuncSetAttribute(word_encode_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(word_encode_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmemBytes);
+    cudaFuncSetAttribute(word_encode_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(word_encode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmemBytes);
+    cudaFuncSetAttribute(word_encode_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(word_encode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmemBytes);
+    cudaFuncSetAttribute(word_encode_fused_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(word_encode_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmemBytes);
+    cudaFuncSetAttribute(word_encode_fused_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(word_encode_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmemBytes);
     configure_alias_kernels();
     configure_block_kernels();
     configure_rans64_kernels();
@@ -274,6 +279,18 @@ extern "C" void rb200_model_destroy(rb200_model* m)
     delete m;
 }
 
+namespace {
+// RB200_WORD_RECIPROCAL=33 forces the any-x (33-bit) reciprocal even where the 32-bit one is exact (testing)
+bool word_r32_allowed()
+{
+    static const bool allowed = [] {
+        const char* e = std::getenv("RB200_WORD_RECIPROCAL");
+        return !(e && std::strcmp(e, "33") == 0);
+    }();
+    return allowed;
+}
+}  // namespace
+
 extern "C" int rb200_model_create(rb200_ctx* ctx, int coder, uint32_t scale_bits, const uint32_t freqs[256], rb200_model** out)
 {
     if (!ctx || !freqs || !out) return RB200_E_ARG;
@@ -293,10 +310,12 @@ extern "C" int rb200_model_create(rb200_ctx* ctx, int coder, uint32_t scale_bits
         rc = build_word_device_tables(freqs, *t);
         if (rc == RB200_OK) {
             m->wide = t->wide;
+            m->enc_r32 = t->enc32_ok && word_r32_allowed();
             e = cudaMalloc(&m->d_word_dec, sizeof t->dec);
             if (e == cudaSuccess) e = cudaMalloc(&m->d_word_enc, sizeof t->enc);
             if (e == cudaSuccess) e = cudaMemcpy(m->d_word_dec, t->dec, sizeof t->dec, cudaMemcpyHostToDevice);
-            if (e == cudaSuccess) e = cudaMemcpy(m->d_word_enc, t->enc, sizeof t->enc, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess)
+                e = cudaMemcpy(m->d_word_enc, m->enc_r32 ? t->enc32 : t->enc, sizeof t->enc, cudaMemcpyHostToDevice);
         }
         delete t;
     } else if (coder == RB200_CODER_ALIAS) {
@@ -464,9 +483,10 @@ int encode_word_fused(rb200_ctx* ctx, const rb200_model* model, const uint8_t* d
     uint32_t* counter = static_cast<uint32_t*>(ctx->sizes.p);
     uint64_t* look = reinterpret_cast<uint64_t*>(static_cast<uint8_t*>(ctx->sizes.p) + 16);
     RB_CUDA(ctx, cudaMemsetAsync(ctx->sizes.p, 0, 16 + static_cast<size_t>(n_chunks) * sizeof(uint64_t), ctx->stream));
-    word_encode_fused_kernel<<<grid, kEncWarps * 32, kEncSmemBytes, ctx->stream>>>(
-        d_in, n, chunk_syms, n_chunks, model->d_word_enc, static_cast<uint8_t*>(ctx->scratch.p), slot, look, counter, d_blob, blob_cap,
-        d_offsets, ctx->d_status);
+    auto kernel = model->enc_r32 ? word_encode_fused_kernel<true> : word_encode_fused_kernel<false>;
+    kernel<<<grid, kEncWarps * 32, kEncSmemBytes, ctx->stream>>>(d_in, n, chunk_syms, n_chunks, model->d_word_enc,
+                                                                 static_cast<uint8_t*>(ctx->scratch.p), slot, look, counter, d_blob,
+                                                                 blob_cap, d_offsets, ctx->d_status);
     return check_launch(ctx, "word_encode_fused_kernel");
 }
 
@@ -516,8 +536,9 @@ int encode_device(rb200_ctx* ctx, const rb200_model* model, const uint8_t* d_in,
     if (n_chunks) {
         if (model->coder == RB200_CODER_WORD) {
             const uint32_t grid = (n_chunks + kEncWarps - 1) / kEncWarps;
-            word_encode_kernel<<<grid, kEncWarps * 32, kEncSmemBytes, ctx->stream>>>(d_in, n, chunk_syms, n_chunks, model->d_word_enc,
-                                                                                      scratch, slot, sizes, ctx->d_status);
+            auto kernel = model->enc_r32 ? word_encode_kernel<true> : word_encode_kernel<false>;
+            kernel<<<grid, kEncWarps * 32, kEncSmemBytes, ctx->stream>>>(d_in, n, chunk_syms, n_chunks, model->d_word_enc, scratch, slot,
+                                                                         sizes, ctx->d_status);
             rc = check_launch(ctx, "word_encode_kernel");
         } else if (model->coder == RB200_CODER_ALIAS) {
             rc = launch_alias_encode(ctx->stream, d_in, n, chunk_syms, n_chunks, model->scale_bits, model->d_alias_enc,

@@ -17,11 +17,19 @@ constexpr uint32_t kEncBadSymbol = 0x80000000u;
 // encode: per symbol {magic, freq | start << 13 | shift << 25}: exact division
 //   q = (x + mulhi(x, magic)) >> shift for any 32-bit x (round-up reciprocal),
 //   replacing the hardware divide of RansWordEncPut (rans_word_sse41.h:92).
+//   `enc32` is the same table with a 32-bit reciprocal: the encoder only divides states x < freq << 20
+//   (RansWordEncPut renormalises first), and on that range q = mulhi(x, M32) >> s32 with
+//   M32 = ceil(2^(32+s32) / freq), s32 = ceil(log2 freq) - 1 is exact for every freq <= 2963 and most above
+//   (checked per symbol: (freq * 2^20 - 1) * (M32 * freq - 2^(32+s32)) < 2^(32+s32)); three instructions
+//   fewer per symbol.  freq 1 uses M32 = 2^32 - 1, which yields x - 1; the kernel adds the missing
+//   1 * (4096 - 1) to `start`.  `enc32_ok` says every symbol of the model passed the check.
 struct WordEncEntry { uint32_t magic, packed; };
 struct WordDeviceTables {
     uint32_t dec[4096];
     WordEncEntry enc[256];
+    WordEncEntry enc32[256];
     int wide;
+    int enc32_ok;
 };
 int build_word_device_tables(const uint32_t freqs[256], WordDeviceTables& t);
 

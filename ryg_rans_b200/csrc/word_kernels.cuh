@@ -221,10 +221,14 @@ constexpr uint32_t kEncWarpSmem = kEncStageBytes + kEncRingBytes;            // 
 //   x_max = freq << 20 in 32-bit arithmetic (rans_word_sse41.h:85; wraps to 0 for freq 4096, as the
 //   reference does); its low 20 bits are zero, so the 4-bit reciprocal shift rides in them:
 //   x >= x_max  <=>  (x | 31) >= (x_max | shift), and the funnel shift only looks at the low 5 bits.
+// R32: `e` comes from the 32-bit-reciprocal table (tables.h: enc32).  mulhi(x, 2^32 - 1) = x - 1 for the
+// freq-1 entries, so their `start` carries the missing (4096 - 1).
+template <bool R32>
 __device__ __forceinline__ uint4 word_enc_expand(WordEncEntry e)
 {
     const uint32_t freq = e.packed & 0x1fffu, start = (e.packed >> 13) & 0xfffu, shift = (e.packed >> 25) & 0xfu;
-    return make_uint4(e.magic, (freq << 20) | shift, start, kWordSlots - freq);    // freq 0 (bad symbol) <=> w == 4096
+    const uint32_t fix = (R32 && freq == 1) ? kWordSlots - 1 : 0;
+    return make_uint4(e.magic, (freq << 20) | shift, start + fix, kWordSlots - freq);    // freq 0 (bad symbol) <=> w == 4096
 }
 
 __device__ __forceinline__ uint32_t funnel_shr_wrap(uint32_t lo, uint32_t hi, uint32_t n)
@@ -241,6 +245,7 @@ struct WordEncState {
 };
 
 // RansWordEncPut for 32 lanes (rans_word_sse41.h:81-93)
+template <bool R32>
 __device__ __forceinline__ void word_enc_step(WordEncState& st, uint32_t sym, uint32_t tab_lane, uint32_t ring, uint32_t gt, bool active)
 {
     bool need = false;
@@ -257,10 +262,16 @@ __device__ __forceinline__ void word_enc_step(WordEncState& st, uint32_t sym, ui
     }
     st.wpos -= 2u * __popc(mask);
     if (active) {
-        // q = x / freq exactly: M = 2^32 + magic = ceil(2^(32+shift) / freq), q = (x + mulhi(x, magic)) >> shift
-        const uint32_t hi = __umulhi(st.x, e.x);
-        const uint32_t lo = st.x + hi;
-        const uint32_t q = funnel_shr_wrap(lo, lo < hi ? 1u : 0u, e.y);
+        uint32_t q;
+        if (R32) {
+            // x < freq << 20 here, where the 32-bit reciprocal is exact: q = mulhi(x, M32) >> shift
+            q = funnel_shr_wrap(__umulhi(st.x, e.x), 0u, e.y);
+        } else {
+            // q = x / freq exactly for any x: M = 2^32 + magic = ceil(2^(32+shift) / freq), q = (x + mulhi(x, magic)) >> shift
+            const uint32_t hi = __umulhi(st.x, e.x);
+            const uint32_t lo = st.x + hi;
+            q = funnel_shr_wrap(lo, lo < hi ? 1u : 0u, e.y);
+        }
         st.x = st.x + e.z + q * e.w;                       // ((x / freq) << 12) + x % freq + start, :92
     }
 }
@@ -283,6 +294,7 @@ __device__ __forceinline__ void word_enc_flush(uint32_t produced, uint32_t& flus
 // downwards; returns the stream size in bytes (warp-uniform).
 //   tab  = shared address of the 8x replicated uint4 table
 //   wsm  = shared address of this warp's 1 KiB (stage, then ring; 512-byte aligned)
+template <bool R32>
 __device__ __forceinline__ uint32_t word_encode_stream(const uint8_t* __restrict__ chunk_in, uint32_t m, uint32_t tab, uint32_t wsm,
                                                        uint8_t* __restrict__ slot_end, uint32_t* __restrict__ status)
 {
@@ -306,11 +318,11 @@ __device__ __forceinline__ uint32_t word_encode_stream(const uint8_t* __restrict
     if (rem) {
         const bool active = lane < rem;
         const uint32_t s = active ? chunk_in[static_cast<uint64_t>(steps) * 32 + lane] : 0;
-        word_enc_step(st, s, tab_lane, ring, gt, active);
+        word_enc_step<R32>(st, s, tab_lane, ring, gt, active);
     }
     for (uint32_t g = steps; g > nblk * 16; g--) {
         const uint32_t s = chunk_in[static_cast<uint64_t>(g - 1) * 32 + lane];
-        word_enc_step(st, s, tab_lane, ring, gt, true);
+        word_enc_step<R32>(st, s, tab_lane, ring, gt, true);
         if (((g - 1) & 3) == 0) word_enc_flush(kEncRingBytes - 2 - st.wpos, flushed, ring, slot_end, lane);
     }
     word_enc_flush(kEncRingBytes - 2 - st.wpos, flushed, ring, slot_end, lane);
@@ -330,7 +342,7 @@ __device__ __forceinline__ uint32_t word_encode_stream(const uint8_t* __restrict
         for (int grp = 3; grp >= 0; grp--) {
 #pragma unroll
             for (int j = 3; j >= 0; j--)
-                word_enc_step(st, lds_u8(stage + (grp * 4 + j) * 32 + lane), tab_lane, ring, gt, true);
+                word_enc_step<R32>(st, lds_u8(stage + (grp * 4 + j) * 32 + lane), tab_lane, ring, gt, true);
             // <= 256 bytes per 4 steps; flushing whenever >= 256 are pending keeps the 512-byte ring safe
             if (kEncRingBytes - 2 - st.wpos - flushed >= 256) word_enc_flush(kEncRingBytes - 2 - st.wpos, flushed, ring, slot_end, lane);
         }
@@ -354,17 +366,19 @@ __device__ __forceinline__ uint32_t word_encode_stream(const uint8_t* __restrict
 }
 
 // chunk `chunk` into the end of its own worst-case slot of `scratch`; size to sizes[chunk]
+template <bool R32>
 __device__ __forceinline__ void word_encode_chunk(const uint8_t* __restrict__ chunk_in, uint32_t m, uint32_t chunk,
                                                   uint32_t tab, uint32_t wsm, uint8_t* __restrict__ scratch,
                                                   uint32_t slot_bytes, uint32_t* __restrict__ sizes, uint32_t* __restrict__ status)
 {
-    const uint32_t produced = word_encode_stream(chunk_in, m, tab, wsm, scratch + static_cast<uint64_t>(chunk + 1) * slot_bytes, status);
+    const uint32_t produced = word_encode_stream<R32>(chunk_in, m, tab, wsm, scratch + static_cast<uint64_t>(chunk + 1) * slot_bytes, status);
     if ((threadIdx.x & 31) == 0) sizes[chunk] = produced;
 }
 
 #ifndef RB200_ENC_MINBLOCKS
 #define RB200_ENC_MINBLOCKS 3
 #endif
+template <bool R32>
 __global__ void __launch_bounds__(kEncWarps * 32, RB200_ENC_MINBLOCKS)
 word_encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_syms, uint32_t n_chunks,
                    const WordEncEntry* __restrict__ g_table, uint8_t* __restrict__ scratch, uint32_t slot_bytes,
@@ -372,7 +386,7 @@ word_encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_sy
 {
     extern __shared__ __align__(1024) uint8_t s_enc[];     // [32 KiB table][warps x 1 KiB]
     uint4* s_tab = reinterpret_cast<uint4*>(s_enc);
-    for (uint32_t i = threadIdx.x; i < 256 * kEncReplicas; i += blockDim.x) s_tab[i] = word_enc_expand(g_table[i / kEncReplicas]);
+    for (uint32_t i = threadIdx.x; i < 256 * kEncReplicas; i += blockDim.x) s_tab[i] = word_enc_expand<R32>(g_table[i / kEncReplicas]);
     __syncthreads();
 
     const uint32_t warp = threadIdx.x >> 5;
@@ -380,7 +394,7 @@ word_encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_sy
     if (chunk >= n_chunks) return;
     const uint64_t first = static_cast<uint64_t>(chunk) * chunk_syms;
     const uint32_t m = static_cast<uint32_t>(min(static_cast<uint64_t>(chunk_syms), n - first));
-    word_encode_chunk(in + first, m, chunk, smem_addr(s_enc), smem_addr(s_enc) + kEncTableBytes + warp * kEncWarpSmem, scratch,
+    word_encode_chunk<R32>(in + first, m, chunk, smem_addr(s_enc), smem_addr(s_enc) + kEncTableBytes + warp * kEncWarpSmem, scratch,
                       slot_bytes, sizes, status);
 }
 constexpr uint32_t kEncSmemBytes = kEncTableBytes + kEncWarps * kEncWarpSmem;
@@ -528,6 +542,7 @@ __device__ __forceinline__ void fused_place(const uint64_t* look, uint32_t chunk
 // Grid = resident capacity (SMs x RB200_ENC_MINBLOCKS CTAs).  Warp 0 of CTA 0 is the scanner, every other warp is
 // a worker with TWO scratch slots: it encodes chunk k+1 into one slot before it places chunk k from the other,
 // so by the time it asks for E_k the scanner has normally long passed k and nobody polls.
+template <bool R32>
 __global__ void __launch_bounds__(kEncWarps * 32, RB200_ENC_MINBLOCKS)
 word_encode_fused_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_syms, uint32_t n_chunks,
                          const WordEncEntry* __restrict__ g_table, uint8_t* __restrict__ scratch, uint32_t slot_bytes,
@@ -536,7 +551,7 @@ word_encode_fused_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t ch
 {
     extern __shared__ __align__(1024) uint8_t s_enc[];     // [32 KiB table][warps x 1 KiB]
     uint4* s_tab = reinterpret_cast<uint4*>(s_enc);
-    for (uint32_t i = threadIdx.x; i < 256 * kEncReplicas; i += blockDim.x) s_tab[i] = word_enc_expand(g_table[i / kEncReplicas]);
+    for (uint32_t i = threadIdx.x; i < 256 * kEncReplicas; i += blockDim.x) s_tab[i] = word_enc_expand<R32>(g_table[i / kEncReplicas]);
     __syncthreads();
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -557,7 +572,7 @@ word_encode_fused_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t ch
         const uint64_t first = static_cast<uint64_t>(chunk) * chunk_syms;
         const uint32_t m = static_cast<uint32_t>(min(static_cast<uint64_t>(chunk_syms), n - first));
         uint8_t* slot_end = slots + (parity + 1) * static_cast<uint64_t>(slot_bytes);
-        const uint32_t produced = word_encode_stream(in + first, m, tab, wsm, slot_end, status);
+        const uint32_t produced = word_encode_stream<R32>(in + first, m, tab, wsm, slot_end, status);
         if (lane == 0) st_relaxed_u64(look + chunk, kLookAgg | ((produced + 15u) & ~15u));
         __syncwarp();
         if (pending)

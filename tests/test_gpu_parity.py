@@ -202,7 +202,25 @@ def _block_data(gen, n_blocks, block_size):
 
 @pytest.mark.parametrize("n_blocks,block_size,chunk", [(13, 65536, 8192), (7, 4096, 4096), (6, 16384, 2048), (12, 65536, 65536)])
 def test_block_models_and_roundtrip(gpu_ctx, oracle_lib, gen, n_blocks, block_size, chunk):
-    data = _block_data(gen, n_blocks, block_size)
+    _check_blocks(gpu_ctx, oracle_lib, _block_data(gen, n_blocks, block_size), n_blocks, block_size, chunk)
+
+
+def test_block_reciprocal_fallback(gpu_ctx, oracle_lib, gen):
+    """Per-block encoders pick the 32-bit reciprocal when it is exact for the block's model; blocks whose model has
+    a symbol of frequency 2964 or 3005 (the first that are not) must fall back, next to blocks that do not."""
+    rng = np.random.default_rng(11)
+    blocks = []
+    for f0 in (2964, 16, 3005, 2963):
+        b = np.concatenate([np.full(f0 * 16, 7, np.uint8), np.full((4096 - f0) * 16, 9, np.uint8)])
+        rng.shuffle(b)
+        blocks.append(b)
+    blocks.append(gen("zipf", 65536, 5))
+    data = np.concatenate(blocks)
+    freqs16 = _check_blocks(gpu_ctx, oracle_lib, data, len(blocks), 65536, 8192)
+    assert [int(freqs16[b][7]) for b in range(4)] == [2964, 16, 3005, 2963]
+
+
+def _check_blocks(gpu_ctx, oracle_lib, data, n_blocks, block_size, chunk):
     freqs16 = gpu_ctx.blocks_build_models(data, n_blocks, block_size)
     want = np.stack([oracle_lib.model(data[b * block_size:(b + 1) * block_size], 12)[0] for b in range(n_blocks)])
     assert np.array_equal(freqs16.astype(np.uint32), want), "device normalize_freqs differs from the reference algorithm"
@@ -223,6 +241,7 @@ def test_block_models_and_roundtrip(gpu_ctx, oracle_lib, gen, n_blocks, block_si
     assert np.array_equal(blob, oblob)
     out = gpu_ctx.blocks_decode_host(oblob, ooffs, freqs16, n_blocks, block_size, chunk)
     assert np.array_equal(out, data)
+    return freqs16
 
 
 # ---------------------------------------------------------------- alternative paths, big sizes
@@ -277,6 +296,64 @@ def test_host_pipeline_many_slices(gpu_ctx, oracle_lib, gen):
     out = gpu_ctx.decode_host(model, blob, offs, n, 8192)
     assert np.array_equal(out, data)
     model.close()
+
+
+@pytest.mark.parametrize("f0", [1, 2963, 2964, 3005, 4095])
+def test_word_reciprocal_variants(gpu_ctx, oracle_lib, f0):
+    """The word encoder divides by a 32-bit reciprocal where that is exact on x < freq << 20 (every freq <= 2963 and
+    most above; freq 1 through the x - 1 identity) and by the any-x 33-bit one otherwise (2964 and 3005 are the
+    first frequencies that need it).  Hand-built models put one symbol on exactly that frequency."""
+    rng = np.random.default_rng(f0)
+    freqs = np.zeros(256, np.uint32)
+    freqs[7] = f0
+    rest = 4096 - f0
+    freqs[200] = rest // 2
+    freqs[13] = rest - rest // 2
+    cum = np.concatenate([[0], np.cumsum(freqs)]).astype(np.uint32)
+    p = freqs / 4096.0
+    data = rng.choice(256, 300_011, p=p).astype(np.uint8)
+    data[:2] = (7, 13)                       # both present even when rare
+    model = gpu_ctx.model(WORD, 12, freqs)
+    for chunk in (8192, 999):
+        blob, offs = gpu_ctx.encode_host(model, data, chunk)
+        ob, oo = oracle_lib.chunked_encode(orc.CODER_WORD, data, freqs, cum, chunk)
+        assert np.array_equal(offs, oo) and np.array_equal(blob, ob), (f0, chunk)
+        assert np.array_equal(gpu_ctx.decode_host(model, blob, offs, data.size, chunk), data)
+    model.close()
+
+
+def test_word_reciprocal_forced_33bit():
+    """RB200_WORD_RECIPROCAL=33 forces the any-x reciprocal for every model; the container must not change."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r)
+import oracle, ryg_rans_b200 as rb
+rng = np.random.default_rng(9)
+orc = oracle.Oracle()
+ctx = rb.Context(0)
+for kind in range(3):
+    if kind == 0:
+        data = rng.integers(0, 256, 2_000_003, dtype=np.uint8)
+    elif kind == 1:
+        p = 1.0 / np.arange(1, 257) ** 1.1
+        data = rng.choice(256, 2_000_003, p=p / p.sum()).astype(np.uint8)
+    else:
+        data = rng.choice(256, 2_000_003, p=[0.97] + [0.03 / 255] * 255).astype(np.uint8)
+    f, c = orc.model(data, 12)
+    m = ctx.model(rb.CODER_WORD, 12, f)
+    for chunk in (8192, 2048):
+        blob, offs = ctx.encode_host(m, data, chunk)
+        ob, oo = orc.chunked_encode(rb.CODER_WORD, data, f, c, chunk, scale_bits=12)
+        assert np.array_equal(offs, oo) and np.array_equal(blob, ob), (kind, chunk)
+    m.close()
+print("r33 ok")
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RB200_WORD_RECIPROCAL="33")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "r33 ok" in out.stdout, out.stderr[-2000:]
 
 
 def test_host_pipeline_ramped_slices():
