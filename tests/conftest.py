@@ -56,6 +56,14 @@ def ref_lib():
 
 
 @pytest.fixture(scope="session")
+def cuda_box():
+    """For GPU tests that drive the library from a child process: skip (rather than fail) where there is no GPU."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+@pytest.fixture(scope="session")
 def gpu_ctx():
     import torch
     if not torch.cuda.is_available():

@@ -247,7 +247,7 @@ def _check_blocks(gpu_ctx, oracle_lib, data, n_blocks, block_size, chunk):
 # ---------------------------------------------------------------- alternative paths, big sizes
 
 @pytest.mark.parametrize("path", ["fused", "split"])
-def test_forced_encode_paths(tmp_path, path):
+def test_forced_encode_paths(cuda_box, path):
     """Both word-encode paths (RB200_ENCODE_PATH=fused: persistent encode + scanner warp + deferred placement;
     =split: encode, tile scan, compaction) must produce the identical container at every chunk size."""
     import os
@@ -322,7 +322,7 @@ def test_word_reciprocal_variants(gpu_ctx, oracle_lib, f0):
     model.close()
 
 
-def test_word_reciprocal_forced_33bit():
+def test_word_reciprocal_forced_33bit(cuda_box):
     """RB200_WORD_RECIPROCAL=33 forces the any-x reciprocal for every model; the container must not change."""
     import os
     import subprocess
@@ -356,7 +356,7 @@ print("r33 ok")
     assert out.returncode == 0 and "r33 ok" in out.stdout, out.stderr[-2000:]
 
 
-def test_host_pipeline_ramped_slices():
+def test_host_pipeline_ramped_slices(cuda_box):
     """The host pipeline ramps its first and last three slices (1/8, 1/4, 1/2 of RB200_SLICE_MIB).  With 1 MiB
     slices a 9 MB input takes the ramped plan; the container must not depend on the slicing: equal to the
     oracle's for every coder, also with tiny and ragged chunks and a non-pinned directory."""
@@ -481,7 +481,7 @@ def test_device_pointers_with_offset_views(gpu_ctx, oracle_lib, gen):
 
 
 @pytest.mark.parametrize("coder", ["word", "alias"])
-def test_cpp_driver_exam_gpu(coder):
+def test_cpp_driver_exam_gpu(cuda_box, coder):
     """The reference-style C++ driver (csrc/exam_gpu.cpp) over the C-ABI: host code in C++, no Python in the path."""
     import os
     import subprocess
