@@ -210,6 +210,9 @@ word_decode_kernel(const uint8_t* __restrict__ blob, uint64_t blob_size, const u
 // parameters come from ONE conflict-free LDS.128: the 256-entry table is replicated 8x so
 // that the 8 lanes of a quarter-warp always hit different 16-byte bank groups.
 // ---------------------------------------------------------------------------
+#ifndef RB200_ENC_ASM_RENORM
+#define RB200_ENC_ASM_RENORM 1
+#endif
 constexpr int kEncWarps = 16;
 constexpr uint32_t kEncReplicas = 8;
 constexpr uint32_t kEncStageBytes = 512;     // 16 steps x 32 symbols
@@ -245,7 +248,9 @@ struct WordEncState {
 };
 
 // RansWordEncPut for 32 lanes (rans_word_sse41.h:81-93)
-template <bool R32>
+// FULL: all 32 lanes take part (the caller passes active == true); the ragged first step of a chunk is the only
+// one that does not.
+template <bool R32, bool FULL>
 __device__ __forceinline__ void word_enc_step(WordEncState& st, uint32_t sym, uint32_t tab_lane, uint32_t ring, uint32_t gt, bool active)
 {
     bool need = false;
@@ -255,12 +260,41 @@ __device__ __forceinline__ void word_enc_step(WordEncState& st, uint32_t sym, ui
         st.flags |= e.w;
         need = (st.x | 31u) >= e.y;                                   // x >= ((L >> 12) << 16) * freq, :85
     }
+#if RB200_ENC_ASM_RENORM
+    // the same renormalisation as below with ONE predicate feeding the vote, the store and the shift (the
+    // compiler otherwise evaluates the comparison twice and copies x before shifting it)
+    if (FULL) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            ".reg .b32 m, r, a;\n\t"
+            "setp.ge.u32 p, %2, %3;\n\t"
+            "vote.sync.ballot.b32 m, p, 0xffffffff;\n\t"
+            "and.b32 r, m, %4;\n\t"
+            "popc.b32 r, r;\n\t"
+            "shl.b32 r, r, 1;\n\t"
+            "sub.u32 a, %1, r;\n\t"
+            "and.b32 a, a, %5;\n\t"
+            "or.b32 a, a, %6;\n\t"
+            "@p st.shared.u16 [a], %0;\n\t"
+            "@p shr.u32 %0, %0, 16;\n\t"
+            "popc.b32 m, m;\n\t"
+            "shl.b32 m, m, 1;\n\t"
+            "sub.u32 %1, %1, m;\n\t"
+            "}"
+            : "+r"(st.x), "+r"(st.wpos)
+            : "r"(st.x | 31u), "r"(e.y), "r"(gt), "n"(kEncRingBytes - 1), "r"(ring)
+            : "memory");
+    } else
+#endif
+    {
     const uint32_t mask = __ballot_sync(0xffffffffu, need);
     if (need) {
         sts_u16(ring | ((st.wpos - 2u * __popc(mask & gt)) & (kEncRingBytes - 1)), st.x);   // :86-87, lanes 31..0 downwards
         st.x >>= 16;                                                                        // :88
     }
     st.wpos -= 2u * __popc(mask);
+    }
     if (active) {
         uint32_t q;
         if (R32) {
@@ -318,11 +352,11 @@ __device__ __forceinline__ uint32_t word_encode_stream(const uint8_t* __restrict
     if (rem) {
         const bool active = lane < rem;
         const uint32_t s = active ? chunk_in[static_cast<uint64_t>(steps) * 32 + lane] : 0;
-        word_enc_step<R32>(st, s, tab_lane, ring, gt, active);
+        word_enc_step<R32, false>(st, s, tab_lane, ring, gt, active);
     }
     for (uint32_t g = steps; g > nblk * 16; g--) {
         const uint32_t s = chunk_in[static_cast<uint64_t>(g - 1) * 32 + lane];
-        word_enc_step<R32>(st, s, tab_lane, ring, gt, true);
+        word_enc_step<R32, true>(st, s, tab_lane, ring, gt, true);
         if (((g - 1) & 3) == 0) word_enc_flush(kEncRingBytes - 2 - st.wpos, flushed, ring, slot_end, lane);
     }
     word_enc_flush(kEncRingBytes - 2 - st.wpos, flushed, ring, slot_end, lane);
@@ -342,7 +376,7 @@ __device__ __forceinline__ uint32_t word_encode_stream(const uint8_t* __restrict
         for (int grp = 3; grp >= 0; grp--) {
 #pragma unroll
             for (int j = 3; j >= 0; j--)
-                word_enc_step<R32>(st, lds_u8(stage + (grp * 4 + j) * 32 + lane), tab_lane, ring, gt, true);
+                word_enc_step<R32, true>(st, lds_u8(stage + (grp * 4 + j) * 32 + lane), tab_lane, ring, gt, true);
             // <= 256 bytes per 4 steps; flushing whenever >= 256 are pending keeps the 512-byte ring safe
             if (kEncRingBytes - 2 - st.wpos - flushed >= 256) word_enc_flush(kEncRingBytes - 2 - st.wpos, flushed, ring, slot_end, lane);
         }
