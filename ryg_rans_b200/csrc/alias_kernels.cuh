@@ -178,29 +178,70 @@ struct AliasEncState {
 //   ALIAS:  RansEncPutAlias (main_alias.cpp:241-250); table {magic, freq, cum, shift}
 //   !ALIAS: RansEncPutSymbol (rans_byte.h:258-280);   table {x_max, rcp_freq, bias, cmpl_freq | rcp_shift << 16}
 //           = RansEncSymbol (rans_byte.h:159-165), bit 31 of the last word marks a symbol outside the model
-template <bool ALIAS>
+// FULL: all 32 lanes take part (active == true at compile time); only the ragged first step of a chunk does not.
+template <bool ALIAS, bool FULL>
 __device__ __forceinline__ void alias_enc_step(AliasEncState& st, uint32_t sym, uint32_t tab_lane, uint32_t remap, uint32_t ring,
                                                uint32_t gt, uint32_t sb, bool active)
 {
     bool n1 = false, n2 = false;
     uint4 e = make_uint4(0, 1, 0, 0);
+    uint32_t x_max = 0;
     if (active) {
         e = lds_u128_ro(tab_lane + sym * (kEncReplicas * 16));
         st.flags |= e.w;
-        const uint32_t x_max = ALIAS ? e.y << (31 - sb) : e.x;   // ((L >> sb) << 8) * freq, rans_byte.h:64 / :197
-        n1 = st.x >= x_max;                                       // :65 / :265
-        n2 = (st.x >> 8) >= x_max;                                // second trip of the do/while, :67-70
+        x_max = ALIAS ? e.y << (31 - sb) : e.x;                   // ((L >> sb) << 8) * freq, rans_byte.h:64 / :197
     }
-    const uint32_t m1 = __ballot_sync(0xffffffffu, n1);
-    const uint32_t m2 = __ballot_sync(0xffffffffu, n2);
-    if (n1) {
-        // lanes are visited 31..0 (main_alias.cpp:365-370 generalised); each writes downwards
-        const uint32_t pos = st.wpos - __popc(m1 & gt) - __popc(m2 & gt);
-        sts_u8(ring | (pos & (kEncRingBytes - 1)), st.x);                          // :68
-        if (n2) sts_u8(ring | ((pos - 1) & (kEncRingBytes - 1)), st.x >> 8);
-        st.x >>= n2 ? 16 : 8;                                                      // :69
+    if (FULL) {
+        // the renormalisation below as one PTX sequence: two predicates feed the votes, the ranked stores and
+        // the shifts (the compiler otherwise re-evaluates the comparisons and branches around the stores)
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p1, p2;\n\t"
+            ".reg .b32 m1, m2, r1, r2, a, b, xs;\n\t"
+            "shr.u32 xs, %0, 8;\n\t"
+            "setp.ge.u32 p1, %0, %2;\n\t"
+            "setp.ge.u32 p2, xs, %2;\n\t"
+            "vote.sync.ballot.b32 m1, p1, 0xffffffff;\n\t"
+            "vote.sync.ballot.b32 m2, p2, 0xffffffff;\n\t"
+            "and.b32 r1, m1, %3;\n\t"
+            "and.b32 r2, m2, %3;\n\t"
+            "popc.b32 r1, r1;\n\t"
+            "popc.b32 r2, r2;\n\t"
+            "sub.u32 a, %1, r1;\n\t"
+            "sub.u32 a, a, r2;\n\t"
+            "sub.u32 b, a, 1;\n\t"
+            "and.b32 a, a, %4;\n\t"
+            "and.b32 b, b, %4;\n\t"
+            "or.b32 a, a, %5;\n\t"
+            "or.b32 b, b, %5;\n\t"
+            "@p1 st.shared.u8 [a], %0;\n\t"
+            "@p2 st.shared.u8 [b], xs;\n\t"
+            "@p1 mov.b32 %0, xs;\n\t"
+            "@p2 shr.u32 %0, %0, 8;\n\t"
+            "popc.b32 m1, m1;\n\t"
+            "popc.b32 m2, m2;\n\t"
+            "sub.u32 %1, %1, m1;\n\t"
+            "sub.u32 %1, %1, m2;\n\t"
+            "}"
+            : "+r"(st.x), "+r"(st.wpos)
+            : "r"(x_max), "r"(gt), "n"(kEncRingBytes - 1), "r"(ring)
+            : "memory");
+    } else {
+        if (active) {
+            n1 = st.x >= x_max;                                   // :65 / :265
+            n2 = (st.x >> 8) >= x_max;                            // second trip of the do/while, :67-70
+        }
+        const uint32_t m1 = __ballot_sync(0xffffffffu, n1);
+        const uint32_t m2 = __ballot_sync(0xffffffffu, n2);
+        if (n1) {
+            // lanes are visited 31..0 (main_alias.cpp:365-370 generalised); each writes downwards
+            const uint32_t pos = st.wpos - __popc(m1 & gt) - __popc(m2 & gt);
+            sts_u8(ring | (pos & (kEncRingBytes - 1)), st.x);                          // :68
+            if (n2) sts_u8(ring | ((pos - 1) & (kEncRingBytes - 1)), st.x >> 8);
+            st.x >>= n2 ? 16 : 8;                                                      // :69
+        }
+        st.wpos -= __popc(m1) + __popc(m2);
     }
-    st.wpos -= __popc(m1) + __popc(m2);
     if (active) {
         if (ALIAS) {
             // exact x / freq with the 33-bit round-up reciprocal 2^32 + magic, as in the word encoder; here
@@ -241,11 +282,11 @@ __device__ __forceinline__ uint32_t alias_encode_stream(const uint8_t* __restric
     if (rem) {
         const bool active = lane < rem;
         const uint32_t s = active ? chunk_in[static_cast<uint64_t>(steps) * 32 + lane] : 0;
-        alias_enc_step<ALIAS>(st, s, tab_lane, remap, ring, gt, sb, active);
+        alias_enc_step<ALIAS, false>(st, s, tab_lane, remap, ring, gt, sb, active);
     }
     for (uint32_t g = steps; g > nblk * 16; g--) {
         const uint32_t s = chunk_in[static_cast<uint64_t>(g - 1) * 32 + lane];
-        alias_enc_step<ALIAS>(st, s, tab_lane, remap, ring, gt, sb, true);
+        alias_enc_step<ALIAS, true>(st, s, tab_lane, remap, ring, gt, sb, true);
         if (((g - 1) & 3) == 0) word_enc_flush(kEncRingBytes - 1 - st.wpos, flushed, ring, slot_end, lane);
     }
     word_enc_flush(kEncRingBytes - 1 - st.wpos, flushed, ring, slot_end, lane);
@@ -265,7 +306,7 @@ __device__ __forceinline__ uint32_t alias_encode_stream(const uint8_t* __restric
         for (int grp = 3; grp >= 0; grp--) {
 #pragma unroll
             for (int j = 3; j >= 0; j--)
-                alias_enc_step<ALIAS>(st, lds_u8(stage + (grp * 4 + j) * 32 + lane), tab_lane, remap, ring, gt, sb, true);
+                alias_enc_step<ALIAS, true>(st, lds_u8(stage + (grp * 4 + j) * 32 + lane), tab_lane, remap, ring, gt, sb, true);
             if (kEncRingBytes - 1 - st.wpos - flushed >= 256) word_enc_flush(kEncRingBytes - 1 - st.wpos, flushed, ring, slot_end, lane);
         }
     }
