@@ -380,6 +380,9 @@ def run_ours(args, rank, local_rank, world):
     # ---- e2e: host pointers through the C-ABI, copies inside the timed region
     e2e = None
     if args.e2e_steps > 0 and not blocks:
+        # first-touch the pinned buffers on the GPU's own NUMA node (what `numactl --cpunodebind` would do for a
+        # caller); with 8 ranks the copies otherwise cross the socket interconnect
+        numa_node, saved_affinity = bind_to_gpu_numa_node(local_rank)
         h_in = torch.empty(n, dtype=torch.uint8).pin_memory()
         h_in.copy_(data)
         h_blob = torch.empty(cap, dtype=torch.uint8).pin_memory()
@@ -408,7 +411,9 @@ def run_ours(args, rank, local_rank, world):
         et = torch.tensor([dt], dtype=torch.float64, device=dev)
         if dist:
             dist.all_reduce(et, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * n * args.e2e_steps / et.item() / 1e9, "unit": UNIT,
+        if saved_affinity is not None:
+            os.sched_setaffinity(0, saved_affinity)
+        e2e = {"value": world * n * args.e2e_steps / et.item() / 1e9, "unit": UNIT, "host_numa_node": numa_node,
                "h2d_bytes_per_step": int(n + size.value + 8 * (n_chunks + 1)), "d2h_bytes_per_step": int(size.value + n + 8 * (n_chunks + 1)),
                "steps": args.e2e_steps, "note": "rb200_encode + rb200_decode with RB200_MEM_HOST on pinned buffers, wall clock"}
 
@@ -460,6 +465,38 @@ def run_ours(args, rank, local_rank, world):
     if dist:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def bind_to_gpu_numa_node(dev_index):
+    """Restrict this process to the CPUs of the NUMA node GPU `dev_index` hangs off.  Returns (node, previous
+    affinity) or (None, None) when the topology cannot be read; the caller restores the affinity."""
+    try:
+        import torch
+        props = torch.cuda.get_device_properties(dev_index)
+        if hasattr(props, "pci_bus_id"):
+            bdf = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        else:
+            bdf = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(dev_index)],
+                                 capture_output=True, text=True, timeout=20).stdout.strip().lower()[-12:]
+        path = "/sys/bus/pci/devices/%s/numa_node" % bdf
+        node = int(open(path).read())
+        if node < 0:
+            return None, None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus |= set(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        saved = os.sched_getaffinity(0)
+        cpus &= saved
+        if not cpus:
+            return None, None
+        os.sched_setaffinity(0, cpus)
+        return node, saved
+    except Exception:  # noqa: BLE001 -- topology files are optional
+        return None, None
 
 
 def main():
