@@ -57,6 +57,14 @@ def parse_args():
 
 # ------------------------------------------------------------------ synthetic data
 
+def text_probs():
+    """Order-0 distribution of the reference's test file book1 (82 symbols, 4.527 bit/symbol),
+    from the committed fixture tests/golden/book1_hist.json (made by tests/golden/make_book1_hist.py)."""
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests", "golden", "book1_hist.json")) as f:
+        counts = np.asarray(json.load(f)["counts"], dtype=np.float64)
+    return counts / counts.sum()
+
+
 def synth_torch(kind, n, seed, device):
     """Seeded synthetic symbols generated on the device (so 1 GiB need not cross PCIe)."""
     import torch
@@ -81,10 +89,7 @@ def synth_torch(kind, n, seed, device):
     if kind == "zipf":
         p = 1.0 / torch.arange(1, 257, dtype=torch.float64) ** 1.1
     elif kind == "text":
-        rng = np.random.default_rng(98)
-        pp = np.zeros(256)
-        pp[np.random.default_rng(99).permutation(256)[:82]] = rng.dirichlet(np.full(82, 0.35))
-        p = torch.from_numpy(pp)
+        p = torch.from_numpy(text_probs())
     else:
         raise ValueError(kind)
     cdf = torch.cumsum(p / p.sum(), 0).to(device=device, dtype=torch.float32)
@@ -104,8 +109,7 @@ def synth_numpy(kind, n, seed):
     if kind == "zipf":
         p = 1.0 / np.arange(1, 257) ** 1.1
     else:
-        p = np.zeros(256)
-        p[np.random.default_rng(99).permutation(256)[:82]] = np.random.default_rng(98).dirichlet(np.full(82, 0.35))
+        p = text_probs()
     cdf = np.cumsum(p / p.sum())
     out = np.empty(n, np.uint8)
     step = 1 << 24

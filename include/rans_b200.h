@@ -136,6 +136,17 @@ int rb200_decode(rb200_ctx* ctx, const rb200_model* model,
  * counts[256] is written to HOST memory, the call synchronises. */
 int rb200_histogram(rb200_ctx* ctx, const uint8_t* in, size_t n, uint64_t counts[256], int mem_kind);
 
+/* The whole model set-up of the drivers in one call, with the pass over the data on the GPU
+ * (SURVEY 8f.1): stats.count_freqs (main.cpp:59-66; rb200_histogram's kernel), then
+ * stats.normalize_freqs(1 << scale_bits) (main.cpp:75-129; 256 counters, on the host, the
+ * reference's algorithm verbatim), then the table build of rb200_model_create.  Replaces
+ * main_simd.cpp:131-143 / main.cpp:138-162 / main_alias.cpp:276-282.  freqs_out[256] (may be
+ * NULL) receives the normalised frequencies -- the model a decoder needs.  n must be below
+ * 2^32 like the reference's 32-bit histogram (RB200_E_ARG otherwise); an empty input or one
+ * the reference would assert on is RB200_E_MODEL.  The call synchronises. */
+int rb200_model_from_data(rb200_ctx* ctx, int coder, uint32_t scale_bits, const uint8_t* data, size_t n,
+                          int mem_kind, uint32_t freqs_out[256], rb200_model** out);
+
 /* ---------------------------------------------------------------- per-block models */
 
 /* BASELINE config 5: n_blocks independent blocks of block_size symbols, each with

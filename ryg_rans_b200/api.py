@@ -38,6 +38,8 @@ EXPORTS = [
     ("rb200_decode", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.c_void_p,
                                C.c_size_t, C.c_int]),
     ("rb200_histogram", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, _u64p, C.c_int]),
+    ("rb200_model_from_data", C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_size_t, C.c_int, _u32p,
+                                        C.POINTER(C.c_void_p)]),
     ("rb200_blocks_build_models", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int]),
     ("rb200_blocks_encode", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p,
                                       C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t), C.c_int]),
@@ -294,15 +296,34 @@ class Context:
 
 
 class Model:
-    def __init__(self, ctx, coder, scale_bits, freqs):
+    def __init__(self, ctx, coder, scale_bits, freqs, _handle=None):
         self.ctx = ctx
         self.coder = coder
         self.scale_bits = scale_bits
         freqs = np.ascontiguousarray(freqs, dtype=np.uint32)
         assert freqs.size == 256
+        self.freqs = freqs
+        if _handle is not None:
+            self.h = _handle
+            return
         h = C.c_void_p()
         ctx.lib.check(ctx.lib.dll.rb200_model_create(ctx.h, coder, scale_bits, freqs.ctypes.data_as(_u32p), C.byref(h)), ctx.h)
         self.h = h
+
+    @classmethod
+    def from_data(cls, ctx, coder, scale_bits, data=None, device_ptr=None, n=None):
+        """rb200_model_from_data: histogram on the GPU + the reference's normalize_freqs + tables.  Pass a host
+        array as `data`, or `device_ptr` + `n` for symbols that already live on the device."""
+        freqs = np.zeros(256, np.uint32)
+        h = C.c_void_p()
+        if device_ptr is None:
+            data = np.ascontiguousarray(data, dtype=np.uint8)
+            ptr, n, kind = _np_ptr(data), data.size, MEM_HOST
+        else:
+            ptr, kind = device_ptr, MEM_DEVICE
+        ctx.lib.check(ctx.lib.dll.rb200_model_from_data(ctx.h, coder, scale_bits, ptr, n, kind, freqs.ctypes.data_as(_u32p),
+                                                        C.byref(h)), ctx.h)
+        return cls(ctx, coder, scale_bits, freqs, _handle=h)
 
     def close(self):
         if getattr(self, "h", None) and getattr(self.ctx, "h", None):

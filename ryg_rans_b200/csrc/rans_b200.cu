@@ -854,6 +854,24 @@ extern "C" int rb200_histogram(rb200_ctx* ctx, const uint8_t* in, size_t n, uint
     return RB200_OK;
 }
 
+extern "C" int rb200_model_from_data(rb200_ctx* ctx, int coder, uint32_t scale_bits, const uint8_t* data, size_t n, int mem_kind,
+                                     uint32_t freqs_out[256], rb200_model** out)
+{
+    if (!ctx || !out || (!data && n) || scale_bits < 8 || scale_bits > 16) return RB200_E_ARG;
+    if (n >> 32) return RB200_E_ARG;                 // the reference counts in 32 bits (main.cpp:52)
+    if (n == 0) return RB200_E_MODEL;                // normalize_freqs divides by the total
+    uint64_t counts[256];
+    int rc = rb200_histogram(ctx, data, n, counts, mem_kind);
+    if (rc != RB200_OK) return rc;
+    uint32_t freqs[256], cum[257];
+    for (int s = 0; s < 256; s++) freqs[s] = static_cast<uint32_t>(counts[s]);
+    rc = rb200_normalize_freqs(freqs, cum, 1u << scale_bits);
+    if (rc != RB200_OK) return rc;
+    rc = rb200_model_create(ctx, coder, scale_bits, freqs, out);
+    if (rc == RB200_OK && freqs_out) std::memcpy(freqs_out, freqs, sizeof freqs);
+    return rc;
+}
+
 extern "C" int rb200_blocks_build_models(rb200_ctx* ctx, const uint8_t* in, uint32_t n_blocks, uint32_t block_size,
                                          uint16_t* block_freqs, int mem_kind)
 {

@@ -195,6 +195,40 @@ def test_histogram(gpu_ctx, gen, n):
     assert np.array_equal(counts, np.bincount(data, minlength=256).astype(np.uint64))
 
 
+@pytest.mark.parametrize("coder,sb", [(WORD, 12), (BYTE, 14), (ALIAS, 16), (RANS64, 14)])
+@pytest.mark.parametrize("kind,n", [("text", 300_001), ("two", 4097), ("uniform", 1 << 20)])
+def test_model_from_data(gpu_ctx, oracle_lib, gen, coder, sb, kind, n):
+    """rb200_model_from_data = device histogram + the reference's normalize_freqs + tables: the frequencies it
+    reports are the oracle's, and a stream encoded with that model is the oracle's stream."""
+    import ryg_rans_b200 as rb
+    data = gen(kind, n, 21)
+    freqs, cum = _model(oracle_lib, data, sb)
+    model = rb.Model.from_data(gpu_ctx, coder, sb, data)
+    assert np.array_equal(model.freqs, freqs)
+    blob, offs = gpu_ctx.encode_host(model, data, 8192)
+    ob, oo = oracle_lib.chunked_encode({WORD: orc.CODER_WORD, BYTE: orc.CODER_BYTE, ALIAS: orc.CODER_ALIAS,
+                                        RANS64: orc.CODER_RANS64}[coder], data, freqs, cum, 8192, scale_bits=sb)
+    assert np.array_equal(offs, oo) and np.array_equal(blob, ob)
+    assert np.array_equal(gpu_ctx.decode_host(model, blob, offs, n, 8192), data)
+    model.close()
+
+
+def test_model_from_data_device_and_errors(gpu_ctx, oracle_lib, gen):
+    import torch
+    import ryg_rans_b200 as rb
+    data = gen("zipf", 777_777, 22)
+    d = torch.from_numpy(data).cuda()
+    model = rb.Model.from_data(gpu_ctx, WORD, 12, device_ptr=d.data_ptr(), n=d.numel())
+    assert np.array_equal(model.freqs, _model(oracle_lib, data, 12)[0])
+    model.close()
+    with pytest.raises(rb.RansError) as e:                         # empty input: nothing to normalise
+        rb.Model.from_data(gpu_ctx, WORD, 12, np.zeros(0, np.uint8))
+    assert e.value.code == -2
+    with pytest.raises(rb.RansError) as e:                         # scale_bits below 8: 256 symbols cannot fit 2^7 slots
+        rb.Model.from_data(gpu_ctx, BYTE, 7, gen("uniform", 4096, 1))
+    assert e.value.code == -1
+
+
 def _block_data(gen, n_blocks, block_size):
     kinds = ["zipf", "uniform", "text", "two", "skew", "const"]
     return np.concatenate([gen(kinds[b % len(kinds)], block_size, seed=1000 + b) for b in range(n_blocks)])
