@@ -28,7 +28,8 @@ constexpr uint32_t kAliasDecReplicas = 8;    // quarter-warp lanes hit 8 differe
 //           rans_byte.h:291-304); tab_lane = shared address of cum2sym[1 << sb], followed by the
 //           256 x {start | freq << 16} table.
 // then RansDecRenorm (rans_byte.h:307-318) for both.
-template <bool ALIAS>
+// FULL: all 32 lanes take part (active == true at compile time); only the ragged last step of a chunk does not.
+template <bool ALIAS, bool FULL>
 __device__ __forceinline__ void alias_dec_step(uint32_t& x, uint32_t& cursor, uint32_t tab_lane, uint32_t ring, uint8_t* o,
                                                uint32_t lt, uint32_t sb, bool active)
 {
@@ -51,6 +52,42 @@ __device__ __forceinline__ void alias_dec_step(uint32_t& x, uint32_t& cursor, ui
         }
         n1 = x < kByteL;
         n2 = x < (kByteL >> 8);
+    }
+    if (FULL) {
+        // RansDecRenorm for the warp as one PTX sequence: two predicates feed the votes, the two ranked byte
+        // loads and the state updates (the C++ below costs six more instructions and a branch per step)
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p1, p2;\n\t"
+            ".reg .b32 m, r, a, b;\n\t"
+            "setp.lt.u32 p1, %0, %2;\n\t"
+            "setp.lt.u32 p2, %0, %3;\n\t"
+            "vote.sync.ballot.b32 m, p1, 0xffffffff;\n\t"
+            "and.b32 r, m, %4;\n\t"
+            "popc.b32 r, r;\n\t"
+            "add.u32 a, %1, r;\n\t"
+            "popc.b32 m, m;\n\t"
+            "add.u32 %1, %1, m;\n\t"
+            "vote.sync.ballot.b32 m, p2, 0xffffffff;\n\t"
+            "and.b32 r, m, %4;\n\t"
+            "popc.b32 r, r;\n\t"
+            "add.u32 a, a, r;\n\t"
+            "popc.b32 m, m;\n\t"
+            "add.u32 %1, %1, m;\n\t"
+            "add.u32 b, a, 1;\n\t"
+            "and.b32 a, a, %5;\n\t"
+            "and.b32 b, b, %5;\n\t"
+            "or.b32 a, a, %6;\n\t"
+            "or.b32 b, b, %6;\n\t"
+            "@p1 ld.shared.u8 a, [a];\n\t"
+            "@p2 ld.shared.u8 b, [b];\n\t"
+            "@p1 mad.lo.u32 %0, %0, 256, a;\n\t"
+            "@p2 mad.lo.u32 %0, %0, 256, b;\n\t"
+            "}"
+            : "+r"(x), "+r"(cursor)
+            : "n"(kByteL), "n"(kByteL >> 8), "r"(lt), "n"(kRingBytes - 1), "r"(ring)
+            : "memory");
+        return;
     }
     const uint32_t m1 = __ballot_sync(0xffffffffu, n1);
     const uint32_t m2 = __ballot_sync(0xffffffffu, n2);
@@ -116,32 +153,32 @@ alias_decode_kernel(const uint8_t* __restrict__ blob, uint64_t blob_size, const 
     uint32_t g = 0;
     for (; g + 8 <= steps; g += 8) {
         win.top_up(cursor, lane);
-        alias_dec_step<ALIAS>(x, cursor, tab_lane, win.ring, o, lt, sb, true);
-        alias_dec_step<ALIAS>(x, cursor, tab_lane, win.ring, o + 32, lt, sb, true);
-        alias_dec_step<ALIAS>(x, cursor, tab_lane, win.ring, o + 64, lt, sb, true);
-        alias_dec_step<ALIAS>(x, cursor, tab_lane, win.ring, o + 96, lt, sb, true);
+        alias_dec_step<ALIAS, true>(x, cursor, tab_lane, win.ring, o, lt, sb, true);
+        alias_dec_step<ALIAS, true>(x, cursor, tab_lane, win.ring, o + 32, lt, sb, true);
+        alias_dec_step<ALIAS, true>(x, cursor, tab_lane, win.ring, o + 64, lt, sb, true);
+        alias_dec_step<ALIAS, true>(x, cursor, tab_lane, win.ring, o + 96, lt, sb, true);
         win.top_up(cursor, lane);
-        alias_dec_step<ALIAS>(x, cursor, tab_lane, win.ring, o + 128, lt, sb, true);
-        alias_dec_step<ALIAS>(x, cursor, tab_lane, win.ring, o + 160, lt, sb, true);
-        alias_dec_step<ALIAS>(x, cursor, tab_lane, win.ring, o + 192, lt, sb, true);
-        alias_dec_step<ALIAS>(x, cursor, tab_lane, win.ring, o + 224, lt, sb, true);
+        alias_dec_step<ALIAS, true>(x, cursor, tab_lane, win.ring, o + 128, lt, sb, true);
+        alias_dec_step<ALIAS, true>(x, cursor, tab_lane, win.ring, o + 160, lt, sb, true);
+        alias_dec_step<ALIAS, true>(x, cursor, tab_lane, win.ring, o + 192, lt, sb, true);
+        alias_dec_step<ALIAS, true>(x, cursor, tab_lane, win.ring, o + 224, lt, sb, true);
         o += 256;
     }
     if (g + 4 <= steps) {
         win.top_up(cursor, lane);
-        alias_dec_step<ALIAS>(x, cursor, tab_lane, win.ring, o, lt, sb, true);
-        alias_dec_step<ALIAS>(x, cursor, tab_lane, win.ring, o + 32, lt, sb, true);
-        alias_dec_step<ALIAS>(x, cursor, tab_lane, win.ring, o + 64, lt, sb, true);
-        alias_dec_step<ALIAS>(x, cursor, tab_lane, win.ring, o + 96, lt, sb, true);
+        alias_dec_step<ALIAS, true>(x, cursor, tab_lane, win.ring, o, lt, sb, true);
+        alias_dec_step<ALIAS, true>(x, cursor, tab_lane, win.ring, o + 32, lt, sb, true);
+        alias_dec_step<ALIAS, true>(x, cursor, tab_lane, win.ring, o + 64, lt, sb, true);
+        alias_dec_step<ALIAS, true>(x, cursor, tab_lane, win.ring, o + 96, lt, sb, true);
         o += 128;
         g += 4;
     }
     win.top_up(cursor, lane);
     for (; g < steps; g++) {
-        alias_dec_step<ALIAS>(x, cursor, tab_lane, win.ring, o, lt, sb, true);
+        alias_dec_step<ALIAS, true>(x, cursor, tab_lane, win.ring, o, lt, sb, true);
         o += 32;
     }
-    if (rem) alias_dec_step<ALIAS>(x, cursor, tab_lane, win.ring, o, lt, sb, lane < rem);
+    if (rem) alias_dec_step<ALIAS, false>(x, cursor, tab_lane, win.ring, o, lt, sb, lane < rem);
 
     const bool bad = (cursor != static_cast<uint32_t>(end)) || (x != kByteL);
     if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(status, kStatStream);
