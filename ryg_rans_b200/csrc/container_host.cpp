@@ -35,24 +35,24 @@ struct Header {                 // 64 bytes
 };
 static_assert(sizeof(Header) == 64, "container header must stay 64 bytes");
 
-uint32_t g_crc_table[8][256];
-bool g_crc_ready = false;
-
-void crc_init()
-{
-    for (uint32_t i = 0; i < 256; i++) {
-        uint32_t c = i;
-        for (int k = 0; k < 8; k++) c = (c >> 1) ^ (0xEDB88320u & (0u - (c & 1u)));
-        g_crc_table[0][i] = c;
+struct CrcTable {
+    uint32_t t[8][256];
+    CrcTable()
+    {
+        for (uint32_t i = 0; i < 256; i++) {
+            uint32_t c = i;
+            for (int k = 0; k < 8; k++) c = (c >> 1) ^ (0xEDB88320u & (0u - (c & 1u)));
+            t[0][i] = c;
+        }
+        for (uint32_t i = 0; i < 256; i++)
+            for (int k = 1; k < 8; k++) t[k][i] = (t[k - 1][i] >> 8) ^ t[0][t[k - 1][i] & 0xff];
     }
-    for (uint32_t i = 0; i < 256; i++)
-        for (int t = 1; t < 8; t++) g_crc_table[t][i] = (g_crc_table[t - 1][i] >> 8) ^ g_crc_table[0][g_crc_table[t - 1][i] & 0xff];
-    g_crc_ready = true;
-}
+};
 
 uint32_t crc32_update(uint32_t crc, const void* data, size_t len)     // slicing-by-8
 {
-    if (!g_crc_ready) crc_init();
+    static const CrcTable table;                                      // built once, thread-safe (C++11 static)
+    const uint32_t (*T)[256] = table.t;
     const uint8_t* p = static_cast<const uint8_t*>(data);
     crc = ~crc;
     while (len >= 8) {
@@ -60,12 +60,12 @@ uint32_t crc32_update(uint32_t crc, const void* data, size_t len)     // slicing
         std::memcpy(&a, p, 4);
         std::memcpy(&b, p + 4, 4);
         a ^= crc;
-        crc = g_crc_table[7][a & 0xff] ^ g_crc_table[6][(a >> 8) & 0xff] ^ g_crc_table[5][(a >> 16) & 0xff] ^ g_crc_table[4][a >> 24]
-            ^ g_crc_table[3][b & 0xff] ^ g_crc_table[2][(b >> 8) & 0xff] ^ g_crc_table[1][(b >> 16) & 0xff] ^ g_crc_table[0][b >> 24];
+        crc = T[7][a & 0xff] ^ T[6][(a >> 8) & 0xff] ^ T[5][(a >> 16) & 0xff] ^ T[4][a >> 24]
+            ^ T[3][b & 0xff] ^ T[2][(b >> 8) & 0xff] ^ T[1][(b >> 16) & 0xff] ^ T[0][b >> 24];
         p += 8;
         len -= 8;
     }
-    while (len--) crc = (crc >> 8) ^ g_crc_table[0][(crc ^ *p++) & 0xff];
+    while (len--) crc = (crc >> 8) ^ T[0][(crc ^ *p++) & 0xff];
     return ~crc;
 }
 
@@ -129,7 +129,8 @@ extern "C" int rb200_container_open(const uint8_t* buf, size_t size, rb200_conta
     Header h;
     std::memcpy(&h, buf, sizeof h);
     if (h.magic != kMagic || h.version != kVersion || h.lanes != RB200_LANES || !h.chunk_syms) return RB200_E_STREAM;
-    if (h.n_chunks != (h.n_symbols + h.chunk_syms - 1) / h.chunk_syms || h.n_chunks >= (1ull << 31) || (h.blob_bytes & 15))
+    if (h.n_chunks != h.n_symbols / h.chunk_syms + (h.n_symbols % h.chunk_syms != 0) || h.n_chunks >= (1ull << 31) ||
+        (h.blob_bytes & 15) || h.coder > RB200_CODER_RANS64 || h.scale_bits < 8 || h.scale_bits > 16)
         return RB200_E_STREAM;
     const size_t boff = blob_offset(h.n_chunks);
     if (boff > size || h.blob_bytes > size - boff) return RB200_E_STREAM;

@@ -374,7 +374,7 @@ extern "C" int rb200_model_create(rb200_ctx* ctx, int coder, uint32_t scale_bits
 extern "C" size_t rb200_chunk_count(size_t n, uint32_t chunk_syms)
 {
     if (!chunk_syms) return 0;
-    return (n + chunk_syms - 1) / chunk_syms;
+    return n / chunk_syms + (n % chunk_syms != 0);      // no wrap-around for any n
 }
 
 // A chunk stream never exceeds 512 + 2 * symbols bytes, whatever the coder: the word coder emits

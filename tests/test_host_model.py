@@ -145,3 +145,62 @@ def test_container_pack_open_roundtrip(oracle_lib, gen):
             assert ei.value.code == -4
     with pytest.raises(rb.RansError):
         api.container_open(buf[:200])
+
+
+def _reseal(buf):
+    """Recompute the container's meta CRC (IEEE CRC-32 = zlib's) after editing header / model / directory fields, so
+    that the semantic checks behind the checksum are what rejects the container."""
+    import struct
+    import zlib
+    n_chunks = struct.unpack_from("<Q", buf, 24)[0]
+    hdr = bytearray(buf[:64].tobytes())
+    hdr[44:52] = b"\0" * 8                                   # meta_crc, blob_crc
+    end = 64 + 1024 + 8 * (n_chunks + 1)
+    if end > buf.size:
+        return buf
+    crc = zlib.crc32(bytes(hdr) + buf[64:end].tobytes()) & 0xffffffff
+    struct.pack_into("<I", buf, 44, crc)
+    return buf
+
+
+def test_container_open_rejects_crafted_and_truncated_input(oracle_lib, gen):
+    """The parser is the trust boundary of the wire format: every truncation and every inconsistent field must come
+    back as RB200_E_STREAM (-4) -- with a VALID checksum, so the field checks themselves are exercised -- never as a
+    crash or an out-of-bounds view."""
+    import struct
+    from ryg_rans_b200 import api
+    data = gen("text", 20000, 6)
+    freqs, cum = oracle_lib.model(data, 12)
+    blob, offs = oracle_lib.chunked_encode(orc.CODER_WORD, data, freqs, cum, 4096)
+    good = api.container_pack(rb.CODER_WORD, 12, 4096, data.size, freqs, offs, blob, 0)
+    assert api.container_open(_reseal(good.copy()))[0]["n_symbols"] == data.size      # _reseal reproduces the library's CRC
+
+    def rejected(buf):
+        with pytest.raises(rb.RansError) as ei:
+            api.container_open(buf)
+        return ei.value.code
+
+    for cut in list(range(0, 64 + 1024 + 8 * offs.size + 16, 7)) + [good.size - 16, good.size - 1]:
+        assert rejected(good[:cut].copy()) == -4, cut
+    edits = {
+        "magic": (0, "<I", 0x12345678), "version": (4, "<H", 2), "coder": (6, "<B", 9), "scale_bits": (7, "<B", 3),
+        "lanes": (8, "<I", 64), "chunk_syms zero": (12, "<I", 0), "chunk_syms other": (12, "<I", 2048),
+        "n_symbols huge": (16, "<Q", 2 ** 64 - 1), "n_symbols + 1 chunk": (16, "<Q", data.size + 4096),
+        "n_chunks huge": (24, "<Q", 2 ** 40), "n_chunks 2^31": (24, "<Q", 2 ** 31), "blob_bytes odd": (32, "<Q", blob.size + 8),
+        "blob_bytes beyond the buffer": (32, "<Q", blob.size + 4096), "blob_bytes short": (32, "<Q", blob.size - 16),
+    }
+    for name, (off, fmt, val) in edits.items():
+        bad = good.copy()
+        struct.pack_into(fmt, bad, off, val)
+        assert rejected(_reseal(bad)) == -4, name
+    dir_off = 64 + 1024
+    for name, idx, val in (("directory not monotone", 1, int(offs[2]) + 16), ("last entry != blob size", offs.size - 1, int(offs[-1]) - 16)):
+        bad = good.copy()
+        struct.pack_into("<Q", bad, dir_off + 8 * idx, val)
+        assert rejected(_reseal(bad)) == -4, name
+    # random garbage with a valid magic never gets through either
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        junk = rng.integers(0, 256, int(rng.integers(64, 4096)), dtype=np.uint8)
+        junk[:8] = good[:8]
+        assert rejected(junk) == -4
