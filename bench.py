@@ -419,7 +419,9 @@ def run_ours(args, rank, local_rank, world):
             os.sched_setaffinity(0, saved_affinity)
         e2e = {"value": world * n * args.e2e_steps / et.item() / 1e9, "unit": UNIT, "host_numa_node": numa_node,
                "h2d_bytes_per_step": int(n + size.value + 8 * (n_chunks + 1)), "d2h_bytes_per_step": int(size.value + n + 8 * (n_chunks + 1)),
-               "steps": args.e2e_steps, "note": "rb200_encode + rb200_decode with RB200_MEM_HOST on pinned buffers, wall clock"}
+               "steps": args.e2e_steps, "note": "rb200_encode + rb200_decode with RB200_MEM_HOST on pinned buffers, wall clock",
+               "bound": "PCIe: each call streams its input in and its output back concurrently; with both directions busy the "
+                        "slower one gets 43-47 GB/s on this box (tools/pcie_probe.py, profiles/r1_pcie_copies.log)"}
 
     if rank != 0:
         if dist:
