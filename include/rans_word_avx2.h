@@ -14,8 +14,10 @@
 //   RansWord32DecodeChunk(stream, stream_bytes, &tab, out, m);          // m symbols of one chunk
 //
 // Streams need 16 readable bytes behind their end (the same kind of padding RansSimdDecRenorm asks for,
-// main_simd.cpp:146); inside a container every stream but the last is followed by the next one, and
-// rb200_container_pack output can simply be over-allocated by 16 bytes.
+// main_simd.cpp:146); inside a container every stream but the last is followed by the next one, and a buffer
+// holding rb200_container_pack output can simply be over-allocated by 16 bytes.
+// (A two-__m512i variant with vpexpandd refills was measured at the same speed -- the gathers dominate -- and
+// is not shipped.)
 #ifndef RANS_WORD_AVX2_HEADER
 #define RANS_WORD_AVX2_HEADER
 
@@ -184,6 +186,22 @@ static inline int RansWord32DecodeChunk(const uint8_t* stream, size_t stream_byt
     int ok = 1;
     for (int g = 0; g < 4; g++) ok &= _mm256_movemask_epi8(_mm256_cmpeq_epi32(r.v[g], L)) == -1;
     return ok ? 0 : -1;
+}
+
+// All chunks of a blob + directory as produced by rb200_encode / found by rb200_container_open.  Chunks are
+// independent: callers that want threads split the range [0, n_chunks) themselves.  `blob` needs 16 readable bytes
+// behind its end.  Returns 0, or -(1 + index of the first chunk that failed).
+static inline long RansWord32DecodeChunks(const uint8_t* blob, const uint64_t* offsets, size_t first_chunk, size_t last_chunk,
+                                          uint32_t chunk_syms, size_t n, RansWord32Tables const* tab, uint8_t* out)
+{
+    for (size_t c = first_chunk; c < last_chunk; c++) {
+        const uint64_t lo = offsets[c], end = offsets[c + 1] & ~(uint64_t)15;
+        const size_t first = c * (size_t)chunk_syms;
+        const size_t m = n - first < chunk_syms ? n - first : chunk_syms;
+        if (end < lo) return -(long)(1 + c);
+        if (RansWord32DecodeChunk(blob + lo, (size_t)(end - lo), tab, out + first, m)) return -(long)(1 + c);
+    }
+    return 0;
 }
 
 #endif  // RANS_WORD_AVX2_HEADER

@@ -28,3 +28,12 @@ extern "C" int avx2_decode_container(const uint8_t* blob, const uint64_t* offs, 
     }
     return 0;
 }
+
+extern "C" long decode_chunks(const uint8_t* blob, const uint64_t* offs, size_t n_chunks, uint32_t chunk, size_t n,
+                              const uint32_t* freqs, const uint32_t* cum, uint8_t* out)
+{
+    static RansWord32Tables t32;
+    RansWord32TablesReset(&t32);
+    for (int s = 0; s < 256; s++) if (freqs[s]) RansWord32TablesInitSymbol(&t32, (uint8_t)s, cum[s], freqs[s]);
+    return RansWord32DecodeChunks(blob, offs, 0, n_chunks, chunk, n, &t32, out);
+}

@@ -36,6 +36,8 @@ def consumer(tmp_path_factory):
     lib = C.CDLL(str(so))
     lib.avx2_decode_chunk.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
     lib.avx2_decode_container.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.decode_chunks.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.decode_chunks.restype = C.c_long
     return lib
 
 
@@ -52,6 +54,10 @@ def _decode_container(lib, blob, offs, n, chunk, freqs, cum):
     out = np.zeros(n, np.uint8)
     rc = lib.avx2_decode_container(padded.ctypes.data, offs.ctypes.data, offs.size - 1, chunk, n, freqs.ctypes.data, cum.ctypes.data,
                                    out.ctypes.data)
+    out2 = np.zeros(n, np.uint8)                              # the header's own container loop must agree
+    rc2 = lib.decode_chunks(padded.ctypes.data, offs.ctypes.data, offs.size - 1, chunk, n, freqs.ctypes.data, cum.ctypes.data,
+                            out2.ctypes.data)
+    assert (rc == 0) == (rc2 == 0) and (rc != 0 or np.array_equal(out, out2))
     return rc, out
 
 
