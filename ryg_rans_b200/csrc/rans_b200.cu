@@ -444,11 +444,10 @@ int reserve_encode_workspace(rb200_ctx* ctx, uint32_t n_chunks, uint32_t slot, u
 // chunks of >= 4096 symbols; below that the split path is used.  RB200_ENCODE_PATH=split|fused forces one.
 bool use_fused_encode(uint32_t chunk_syms)
 {
-    static int forced = -2;
-    if (forced == -2) {
+    static const int forced = [] {           // read once; thread-safe static initialisation
         const char* e = std::getenv("RB200_ENCODE_PATH");
-        forced = !e ? -1 : (std::strcmp(e, "fused") == 0 ? 1 : (std::strcmp(e, "split") == 0 ? 0 : -1));
-    }
+        return !e ? -1 : (std::strcmp(e, "fused") == 0 ? 1 : (std::strcmp(e, "split") == 0 ? 0 : -1));
+    }();
     // two worst-case slots per resident warp: keep that scratch below ~2 GB (chunks of <= 64 Ki symbols)
     if (chunk_syms > 65536) return false;
     if (forced >= 0) return forced == 1;
