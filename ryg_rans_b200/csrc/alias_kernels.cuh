@@ -440,17 +440,6 @@ alias_encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_s
                     offsets, lane, status);
 }
 
-inline int alias_sm_count()
-{
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-    }
-    return sms;
-}
-
 inline void configure_alias_kernels()
 {
     cudaFuncSetAttribute(alias_decode_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -465,13 +454,13 @@ inline void configure_alias_kernels()
 
 // remap == nullptr selects the rans_byte cum2sym coder.  look == nullptr: split mode (sizes[] out, one slot per
 // chunk); otherwise fused mode (two slots per resident warp; look/counter zeroed by the caller).
-inline int launch_alias_encode(cudaStream_t stream, const uint8_t* d_in, uint64_t n, uint32_t chunk_syms, uint32_t n_chunks,
+// sms = multiprocessors of the context's device (rb200_ctx keeps it; nothing process-wide is cached here).
+inline int launch_alias_encode(cudaStream_t stream, uint32_t sms, const uint8_t* d_in, uint64_t n, uint32_t chunk_syms, uint32_t n_chunks,
                                uint32_t sb, const AliasEncEntry* enc, const uint16_t* remap, uint8_t* scratch, uint32_t slot,
                                uint32_t* sizes, uint64_t* look, uint32_t* counter, uint8_t* blob, uint64_t blob_cap, uint64_t* offsets,
                                uint32_t* status)
 {
     uint32_t grid = (n_chunks + (look ? 1 : 0) + kAliasEncWarps - 1) / kAliasEncWarps;
-    const uint32_t sms = static_cast<uint32_t>(alias_sm_count());
     if (grid > sms) grid = sms;                       // persistent: one CTA per SM
     if (remap)
         alias_encode_kernel<true><<<grid, kAliasEncWarps * 32, kAliasEncFixedSmem + (2u << sb), stream>>>(
@@ -481,7 +470,7 @@ inline int launch_alias_encode(cudaStream_t stream, const uint8_t* d_in, uint64_
             d_in, n, chunk_syms, n_chunks, sb, enc, nullptr, scratch, slot, sizes, look, counter, blob, blob_cap, offsets, status);
     return 0;
 }
-inline uint32_t alias_fused_slots() { return static_cast<uint32_t>(alias_sm_count()) * kAliasEncWarps * 2; }
+inline uint32_t alias_fused_slots(uint32_t sms) { return sms * kAliasEncWarps * 2; }
 
 inline int launch_alias_decode(cudaStream_t stream, const uint8_t* blob, uint64_t blob_size, const uint64_t* offsets, uint32_t sb,
                                const AliasDecEntry* dec, uint8_t* out, uint64_t n, uint32_t chunk_syms, uint32_t n_chunks,

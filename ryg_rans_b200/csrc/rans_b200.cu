@@ -20,6 +20,7 @@
 #include "rans64_kernels.cuh"
 #include "tables.h"
 #include "word_kernels.cuh"
+#include "word_decode_tma.cuh"
 
 using namespace rb200;
 
@@ -37,6 +38,8 @@ struct rb200_ctx {
     cudaStream_t stream = nullptr;
     uint32_t* d_status = nullptr;     // kStat* bits, OR-ed by kernels
     uint32_t* h_status = nullptr;     // pinned mirror
+    DecodeWork* d_work = nullptr;     // persistent decoder's chunk counter; zero between launches (self-resetting)
+    int sms = 0;                      // multiprocessors of `device`
     uint64_t launches = 0;
     std::string last_error;
     // encode workspaces
@@ -182,9 +185,13 @@ extern "C" int rb200_ctx_create(rb200_ctx** out, int device, void* stream)
     DeviceGuard g(device);
     cudaError_t e = cudaMalloc(&ctx->d_status, sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMemset(ctx->d_status, 0, sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_work, sizeof(DecodeWork));
+    if (e == cudaSuccess) e = cudaMemset(ctx->d_work, 0, sizeof(DecodeWork));
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_status, sizeof(uint32_t));
-    if (e != cudaSuccess) {
+    if (e != cudaSuccess || ctx->sms <= 0) {
         if (ctx->d_status) cudaFree(ctx->d_status);
+        if (ctx->d_work) cudaFree(ctx->d_work);
         delete ctx;
         return RB200_E_CUDA;
     }
@@ -203,6 +210,10 @@ extern "C" int rb200_ctx_create(rb200_ctx** out, int device, void* stream)
         return RB200_E_CUDA;
     }
     // the decoders want the large shared-memory carve-out (tables + per-warp rings)
+    cudaFuncSetAttribute(word_decode_tma_kernel<DecShip, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(word_decode_tma_kernel<DecShip, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DecShip::kSmemBytes);
+    cudaFuncSetAttribute(word_decode_tma_kernel<DecShip, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(word_decode_tma_kernel<DecShip, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DecShip::kSmemBytes);
     cudaFuncSetAttribute(word_decode_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(word_decode_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(word_encode_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -229,6 +240,7 @@ extern "C" void rb200_ctx_destroy(rb200_ctx* ctx)
     release(ctx->scratch); release(ctx->sizes);
     release(ctx->st_in); release(ctx->st_blob); release(ctx->st_offsets); release(ctx->st_out); release(ctx->st_aux);
     if (ctx->d_status) cudaFree(ctx->d_status);
+    if (ctx->d_work) cudaFree(ctx->d_work);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
     if (ctx->h_slice_total) cudaFreeHost(ctx->h_slice_total);
     if (ctx->h_dir) cudaFreeHost(ctx->h_dir);
@@ -260,6 +272,7 @@ extern "C" int rb200_sync(rb200_ctx* ctx)
     RB_CUDA(ctx, cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     RB_CUDA(ctx, cudaMemsetAsync(ctx->d_status, 0, sizeof(uint32_t), ctx->stream));
     RB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (*ctx->h_status) RB_CUDA(ctx, cudaMemsetAsync(ctx->d_work, 0, sizeof(DecodeWork), ctx->stream));   // a kernel may have bailed out
     return status_to_code(*ctx->h_status);
 }
 
@@ -454,20 +467,21 @@ bool use_fused_encode(uint32_t chunk_syms)
     return chunk_syms >= 4096;
 }
 
-int sm_count(int device)
+// RB200_DECODE_PATH=classic selects the round-1 decoder (one CTA per 8 chunks, LDG -> STS window) for A/B runs;
+// the default is the persistent kernel of word_decode_tma.cuh.
+bool use_persistent_decode()
 {
-    static int cached_dev = -1, sms = 0;
-    if (cached_dev != device) {
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) sms = 148;
-        cached_dev = device;
-    }
-    return sms;
+    static const bool persistent = [] {
+        const char* e = std::getenv("RB200_DECODE_PATH");
+        return !(e && std::strcmp(e, "classic") == 0);
+    }();
+    return persistent;
 }
 
 uint32_t fused_word_grid(rb200_ctx* ctx, uint32_t n_chunks)
 {
     const uint32_t want = (n_chunks + 1 + kEncWarps - 1) / kEncWarps;       // + 1: one warp of the grid is the scanner
-    const uint32_t grid = static_cast<uint32_t>(sm_count(ctx->device)) * RB200_ENC_MINBLOCKS;
+    const uint32_t grid = static_cast<uint32_t>(ctx->sms) * RB200_ENC_MINBLOCKS;
     return grid > want ? want : grid;
 }
 
@@ -497,7 +511,7 @@ int reserve_encode(rb200_ctx* ctx, const rb200_model* model, uint32_t n_chunks, 
     const uint32_t slot = slot_bytes_for(chunk_syms);
     if (use_fused_encode(chunk_syms) && model->coder != RB200_CODER_RANS64) {
         const size_t slots = model->coder == RB200_CODER_WORD ? static_cast<size_t>(fused_word_grid(ctx, n_chunks)) * kEncWarps * 2
-                                                              : static_cast<size_t>(alias_fused_slots());
+                                                              : static_cast<size_t>(alias_fused_slots(static_cast<uint32_t>(ctx->sms)));
         int rc = reserve(ctx, ctx->scratch, slots * slot + 16);
         if (rc == RB200_OK) rc = reserve(ctx, ctx->sizes, 16 + static_cast<size_t>(n_chunks) * sizeof(uint64_t));
         return rc;
@@ -517,14 +531,14 @@ int encode_device(rb200_ctx* ctx, const rb200_model* model, const uint8_t* d_in,
         return encode_word_fused(ctx, model, d_in, n, chunk_syms, n_chunks, d_blob, blob_cap, d_offsets);
     const uint32_t slot = slot_bytes_for(chunk_syms);
     if (fused && (model->coder == RB200_CODER_ALIAS || model->coder == RB200_CODER_BYTE)) {
-        int rc = reserve(ctx, ctx->scratch, static_cast<size_t>(alias_fused_slots()) * slot + 16);
+        int rc = reserve(ctx, ctx->scratch, static_cast<size_t>(alias_fused_slots(static_cast<uint32_t>(ctx->sms))) * slot + 16);
         if (rc == RB200_OK) rc = reserve(ctx, ctx->sizes, 16 + static_cast<size_t>(n_chunks) * sizeof(uint64_t));
         if (rc != RB200_OK) return rc;
         uint32_t* counter = static_cast<uint32_t*>(ctx->sizes.p);
         uint64_t* look = reinterpret_cast<uint64_t*>(static_cast<uint8_t*>(ctx->sizes.p) + 16);
         RB_CUDA(ctx, cudaMemsetAsync(ctx->sizes.p, 0, 16 + static_cast<size_t>(n_chunks) * sizeof(uint64_t), ctx->stream));
         const bool alias = model->coder == RB200_CODER_ALIAS;
-        launch_alias_encode(ctx->stream, d_in, n, chunk_syms, n_chunks, model->scale_bits, alias ? model->d_alias_enc : model->d_byte_enc,
+        launch_alias_encode(ctx->stream, static_cast<uint32_t>(ctx->sms), d_in, n, chunk_syms, n_chunks, model->scale_bits, alias ? model->d_alias_enc : model->d_byte_enc,
                             alias ? model->d_alias_remap : nullptr, static_cast<uint8_t*>(ctx->scratch.p), slot, nullptr, look, counter,
                             d_blob, blob_cap, d_offsets, ctx->d_status);
         return check_launch(ctx, alias ? "alias_encode_kernel(fused)" : "byte_encode_kernel(fused)");
@@ -540,11 +554,11 @@ int encode_device(rb200_ctx* ctx, const rb200_model* model, const uint8_t* d_in,
                                                                          sizes, ctx->d_status);
             rc = check_launch(ctx, "word_encode_kernel");
         } else if (model->coder == RB200_CODER_ALIAS) {
-            rc = launch_alias_encode(ctx->stream, d_in, n, chunk_syms, n_chunks, model->scale_bits, model->d_alias_enc,
+            rc = launch_alias_encode(ctx->stream, static_cast<uint32_t>(ctx->sms), d_in, n, chunk_syms, n_chunks, model->scale_bits, model->d_alias_enc,
                                      model->d_alias_remap, scratch, slot, sizes, nullptr, nullptr, nullptr, 0, nullptr, ctx->d_status);
             if (rc == RB200_OK) rc = check_launch(ctx, "alias_encode_kernel");
         } else if (model->coder == RB200_CODER_BYTE) {
-            rc = launch_alias_encode(ctx->stream, d_in, n, chunk_syms, n_chunks, model->scale_bits, model->d_byte_enc, nullptr, scratch,
+            rc = launch_alias_encode(ctx->stream, static_cast<uint32_t>(ctx->sms), d_in, n, chunk_syms, n_chunks, model->scale_bits, model->d_byte_enc, nullptr, scratch,
                                      slot, sizes, nullptr, nullptr, nullptr, 0, nullptr, ctx->d_status);
             if (rc == RB200_OK) rc = check_launch(ctx, "byte_encode_kernel");
         } else {
@@ -565,6 +579,16 @@ int decode_device(rb200_ctx* ctx, const rb200_model* model, const uint8_t* d_blo
     const uint32_t n_chunks = static_cast<uint32_t>(n_chunks_sz);
     if (!n_chunks) return RB200_OK;
     if (model->coder == RB200_CODER_WORD) {
+        if (use_persistent_decode()) {
+            // persistent grid: 2 CTAs of 32 warps per SM, chunks handed out by an atomic counter (word_decode_tma.cuh)
+            const uint32_t want = (n_chunks + DecShip::kWarps - 1) / DecShip::kWarps;
+            const uint32_t full = static_cast<uint32_t>(ctx->sms) * DecShip::kMinBlocks;
+            const uint32_t grid = want < full ? want : full;
+            auto kernel = model->wide ? word_decode_tma_kernel<DecShip, true> : word_decode_tma_kernel<DecShip, false>;
+            kernel<<<grid, DecShip::kWarps * 32, DecShip::kSmemBytes, ctx->stream>>>(d_blob, blob_size, d_offsets, model->d_word_dec, d_out, n,
+                                                                                     chunk_syms, n_chunks, ctx->d_work, ctx->d_status, 0);
+            return check_launch(ctx, "word_decode_tma_kernel");
+        }
         const uint32_t grid = (n_chunks + kDecWarps - 1) / kDecWarps;
         if (model->wide)
             word_decode_kernel<true><<<grid, kDecWarps * 32, 0, ctx->stream>>>(d_blob, blob_size, d_offsets, model->d_word_dec, d_out,

@@ -234,7 +234,10 @@ def _block_data(gen, n_blocks, block_size):
     return np.concatenate([gen(kinds[b % len(kinds)], block_size, seed=1000 + b) for b in range(n_blocks)])
 
 
-@pytest.mark.parametrize("n_blocks,block_size,chunk", [(13, 65536, 8192), (7, 4096, 4096), (6, 16384, 2048), (12, 65536, 65536)])
+@pytest.mark.parametrize("n_blocks,block_size,chunk", [(13, 65536, 8192), (7, 4096, 4096), (6, 16384, 2048), (12, 65536, 65536),
+                                                       (5, 65536, 2048),      # 32 chunks per block: the widest CTA (32 warps)
+                                                       (5, 17 * 1024, 1024)])  # 17 chunks per block: rounds up to 32 warps
+
 def test_block_models_and_roundtrip(gpu_ctx, oracle_lib, gen, n_blocks, block_size, chunk):
     _check_blocks(gpu_ctx, oracle_lib, _block_data(gen, n_blocks, block_size), n_blocks, block_size, chunk)
 
@@ -310,6 +313,53 @@ print("fused ok", ctx.launches)
     env = dict(os.environ, RB200_ENCODE_PATH=path)
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "fused ok" in out.stdout, out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("path", ["classic", "persistent"])
+def test_forced_decode_paths(cuda_box, path):
+    """Both word decoders (RB200_DECODE_PATH=classic: one CTA per 8 chunks, LDG -> STS window; default: persistent grid,
+    TMA-staged table, cp.async ring, word_decode_tma.cuh) must decode oracle containers bit-exactly at every chunk size,
+    ragged tails and the single-symbol (freq 4096) model included, report corruption, and stay usable afterwards (the
+    persistent decoder's work counter re-arms itself)."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r)
+import oracle, ryg_rans_b200 as rb
+rng = np.random.default_rng(11)
+p = 1.0 / np.arange(1, 257) ** 1.1
+orc = oracle.Oracle()
+ctx = rb.Context(0)
+for n in (1, 31, 32, 33, 4097, 1_000_003, 3_000_017):
+    for kind in ("zipf", "uniform", "single"):
+        if kind == "zipf": data = rng.choice(256, n, p=p / p.sum()).astype(np.uint8)
+        elif kind == "uniform": data = rng.integers(0, 256, n, dtype=np.uint8)
+        else: data = np.full(n, 65, np.uint8)
+        f, c = orc.model(data, 12)
+        m = ctx.model(rb.CODER_WORD, 12, f)
+        for chunk in (32, 96, 4096, 8192, 65536):
+            if n > 200_000 and chunk < 4096: continue
+            ob, oo = orc.chunked_encode(oracle.CODER_WORD, data, f, c, chunk, scale_bits=12)
+            for rep in range(2):                      # back to back: the chunk counter must have re-armed
+                assert np.array_equal(ctx.decode_host(m, ob, oo, n, chunk), data), (n, kind, chunk, rep)
+            if n >= 4097 and chunk == 4096:
+                bad = ob.copy()
+                bad[int(oo[0]) + 128:int(oo[0]) + 400] ^= 0x5a          # inside the first chunk's stream
+                try:
+                    ctx.decode_host(m, bad, oo, n, chunk)
+                    raise SystemExit("corruption not reported")
+                except rb.RansError as e:
+                    assert e.code == -4, e
+                assert np.array_equal(ctx.decode_host(m, ob, oo, n, chunk), data)
+        m.close()
+print("decode paths ok", ctx.launches)
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RB200_DECODE_PATH=path)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "decode paths ok" in out.stdout
 
 
 def test_host_pipeline_many_slices(gpu_ctx, oracle_lib, gen):
