@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RB200_VERSION 1
+#define RB200_VERSION 2
 
 /* status codes (the reference only has assert(); SURVEY section 5 asks for codes) */
 #define RB200_OK          0
@@ -41,6 +41,7 @@ extern "C" {
 #define RB200_E_CUDA     -5   /* CUDA runtime error, see rb200_last_cuda_error          */
 #define RB200_E_NOMEM    -6
 #define RB200_E_SYMBOL   -7   /* encoder met a symbol whose model frequency is 0        */
+#define RB200_E_NCCL     -8   /* NCCL missing or an NCCL call failed, see rb200_last_cuda_error */
 
 /* which memory the data pointers of a bulk call live in */
 #define RB200_MEM_HOST    0   /* host pointers; the call copies H2D/D2H and is synchronous */
@@ -164,6 +165,31 @@ int rb200_blocks_encode(rb200_ctx* ctx, const uint8_t* in, uint32_t n_blocks, ui
 int rb200_blocks_decode(rb200_ctx* ctx, const uint8_t* blob, size_t blob_size, const uint64_t* offsets,
                         const uint16_t* block_freqs, uint32_t n_blocks, uint32_t block_size,
                         uint32_t chunk_syms, uint8_t* out, int mem_kind);
+
+/* ---------------------------------------------------------------- multi-GPU: gathering the shards' blobs (NCCL) */
+
+/* Shards are independent: every rank encodes / decodes its own contiguous range of symbols with no
+ * communication.  The one exchange step is collecting the compressed blobs + directories on one rank, which these
+ * calls do over NCCL / NVLink (ncclAllGather of the sizes, then grouped ncclSend / ncclRecv of the payloads straight
+ * into their final position; the directories are rebased on the root).  The concatenation is itself a valid container
+ * because every shard's blob ends 16-byte aligned.  The reference analogue is the driver keeping `rans_begin` per
+ * buffer (main_simd.cpp:287-300); it has no multi-device story.  libnccl.so.2 is loaded on first use (dlopen), so
+ * single-GPU users need no NCCL.
+ *
+ *   rank 0: rb200_comm_unique_id(id)  -> hand the 128 bytes to every rank (file, socket, MPI, torch.distributed ...)
+ *   all   : rb200_comm_create(ctx, id, rank, world, &comm)             (collective: ncclCommInitRank)
+ *   all   : rb200_gather_plan(comm, blob_size, n_chunks, totals)       (collective, synchronises: sizes of every shard)
+ *   all   : rb200_gather_blobs(comm, root, d_blob, d_offsets, d_out_blob, out_cap, d_out_offsets)
+ *           enqueued on the context's stream; only `root` needs the out buffers: totals[0] bytes of blob and
+ *           totals[1] + 1 directory entries.  May be repeated while the planned sizes stay valid. */
+typedef struct rb200_comm rb200_comm;
+#define RB200_NCCL_ID_BYTES 128
+int rb200_comm_unique_id(uint8_t id[RB200_NCCL_ID_BYTES]);
+int rb200_comm_create(rb200_ctx* ctx, const uint8_t id[RB200_NCCL_ID_BYTES], int rank, int world, rb200_comm** out);
+void rb200_comm_destroy(rb200_comm* comm);
+int rb200_gather_plan(rb200_comm* comm, uint64_t blob_size, uint64_t n_chunks, uint64_t totals[2]);
+int rb200_gather_blobs(rb200_comm* comm, int root, const uint8_t* d_blob, const uint64_t* d_offsets,
+                       uint8_t* d_out_blob, uint64_t out_cap, uint64_t* d_out_offsets);
 
 /* ---------------------------------------------------------------- wire format (host only) */
 

@@ -45,6 +45,11 @@ EXPORTS = [
                                       C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t), C.c_int]),
     ("rb200_blocks_decode", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
                                       C.c_uint32, C.c_void_p, C.c_int]),
+    ("rb200_comm_unique_id", C.c_int, [C.c_void_p]),
+    ("rb200_comm_create", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    ("rb200_comm_destroy", None, [C.c_void_p]),
+    ("rb200_gather_plan", C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, _u64p]),
+    ("rb200_gather_blobs", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     ("rb200_container_size", C.c_size_t, [C.c_size_t, C.c_size_t]),
     ("rb200_container_pack", C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.c_size_t, _u32p, C.c_void_p, C.c_void_p, C.c_size_t,
                                        C.c_uint32, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
@@ -111,7 +116,7 @@ class Lib:
     def check(self, rc, ctx=None):
         if rc != 0:
             msg = self.dll.rb200_strerror(rc).decode()
-            if rc == -5 and ctx is not None:
+            if rc in (-5, -8) and ctx is not None:
                 msg += ": " + self.dll.rb200_last_cuda_error(ctx).decode()
             raise RansError(rc, msg)
 

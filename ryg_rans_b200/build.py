@@ -8,6 +8,7 @@ _ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("RB200_LIB") or os.path.join(_HERE, "librans_b200.so")   # RB200_LIB: A/B-test another build
 EXAM_PATH = os.path.join(_HERE, "exam_gpu")
+EXAM_MULTI_PATH = os.path.join(_HERE, "exam_gpu_multi")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -50,4 +51,8 @@ def build(force=False, verbose=False):
     if os.path.exists(exam_src) and (force or _stale(EXAM_PATH)):
         subprocess.check_call([shutil.which("g++") or "g++", "-O2", "-std=c++17", "-I" + os.path.join(_ROOT, "include"),
                                "-o", EXAM_PATH, exam_src, "-L" + _HERE, "-lrans_b200", "-Wl,-rpath,$ORIGIN"])
+    multi_src = os.path.join(CSRC, "exam_gpu_multi.cpp")          # the sharded driver: needs the CUDA runtime for its buffers
+    if os.path.exists(multi_src) and (force or _stale(EXAM_MULTI_PATH)):
+        subprocess.check_call([nvcc, "-Wno-deprecated-gpu-targets", "-O2", "-std=c++17", "-I" + os.path.join(_ROOT, "include"), "-o", EXAM_MULTI_PATH, multi_src,
+                               "-L" + _HERE, "-lrans_b200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"])
     return LIB_PATH

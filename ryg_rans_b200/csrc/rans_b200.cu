@@ -168,6 +168,7 @@ extern "C" const char* rb200_strerror(int code)
     case RB200_E_CUDA: return "CUDA error";
     case RB200_E_NOMEM: return "out of device memory";
     case RB200_E_SYMBOL: return "symbol with zero model frequency";
+    case RB200_E_NCCL: return "NCCL error";
     }
     return "unknown";
 }
@@ -1022,3 +1023,8 @@ extern "C" int rb200_blocks_decode(rb200_ctx* ctx, const uint8_t* blob, size_t b
     RB_CUDA(ctx, cudaMemcpyAsync(out, ctx->st_out.p, n, cudaMemcpyDeviceToHost, ctx->stream));
     return rb200_sync(ctx);
 }
+
+// ---------------------------------------------------------------------------
+// multi-GPU: gathering the shards' blobs over NCCL
+// ---------------------------------------------------------------------------
+#include "gather_nccl.cuh"

@@ -81,7 +81,7 @@ constexpr int kAblNoRefill = 8;             // never wait for / issue ring units
 constexpr int kRefillTma = 0;       // cp.async.bulk (UBLKCP) by one elected lane, mbarrier per slot
 constexpr int kRefillCpAsync = 1;   // cp.async.cg 16 bytes per lane (LDGSTS), commit/wait groups
 
-template <int kWarps_, int kMinBlocks_, int kGroup_, int kRefill_ = kRefillTma, int kUnitLog_ = 9, bool kWideMul_ = true, int kTexEvery_ = 0,
+template <int kWarps_, int kMinBlocks_, int kGroup_, int kRefill_ = kRefillTma, int kUnitLog_ = 9, int kWideMul_ = 0, int kTexEvery_ = 0,
           int kAblate_ = 0, bool kIadd3_ = false>
 struct DecPolicy {
     static constexpr bool kIadd3 = kIadd3_;           // refill address / cursor update as cur + r + r (IADD3, ALU pipe) instead of IMAD
@@ -89,7 +89,7 @@ struct DecPolicy {
     static constexpr int kMinBlocks = kMinBlocks_;    // CTAs per SM the register budget is sized for
     static constexpr int kGroup = kGroup_;            // steps between two fill checks / ring wraps (<= 8)
     static constexpr int kRefill = kRefill_;
-    static constexpr bool kWideMul = kWideMul_;       // field extraction by IMAD.WIDE (see tma_dec_step)
+    static constexpr int kWideMul = kWideMul_;        // field extraction by IMAD.WIDE: bit 0 for the state, bit 1 for the table entry
     static constexpr int kTexEvery = kTexEvery_;      // 0: every gather from shared memory; k: every k-th through the TEX pipe
     static constexpr int kAblate = kAblate_;
     static constexpr uint32_t kUnit = 1u << kUnitLog_;                    // bytes per ring unit (512 or 1024)
@@ -216,14 +216,16 @@ __device__ __forceinline__ void mul_wide_u32(uint32_t a, uint32_t b, uint32_t& l
 //   tab = shared address of the packed table freq << 20 | bias << 8 | symbol.
 //   kWideMul: x * 2^20 as a 64-bit product gives q = x >> 12 in the high word and slot << 20 in the low one, from which
 //   ptxas forms the table address with ONE LEA.HI; e * 2^12 likewise gives freq in the high word and bias << 20 in the
-//   low one.  Two IMAD.WIDE + one shift replace five shift/mask instructions.
+//   low one.  Two IMAD.WIDE + one shift replace five shift/mask instructions (16 instead of 18 per step) -- but they run
+//   on the FMA-heavy pipe, which the four IMADs of the step already load, and measured slower than the shift form
+//   (profiles/r2_decode_lab.md); the shipped configuration uses shifts.
 template <class P, bool WIDE>
 __device__ __forceinline__ void tma_dec_step(uint32_t& x, uint32_t& cur, uint32_t tab, uint8_t* o, uint32_t lt, uint32_t lane,
                                              cudaTextureObject_t tex, bool via_tex, bool active)
 {
     if (active) {
         uint32_t q, f, b, e;
-        if (P::kWideMul && !via_tex) {
+        if ((P::kWideMul & 1) && !via_tex) {
             uint32_t lo;
             mul_wide_u32(x, 1u << 20, lo, q);                                  // q = x >> 12, lo = (x & 4095) << 20
             if (P::kAblate & kAblGatherConflictFree) e = lds_u32_ro(mad_u32(lo >> 25, 128u, tab + lane * 4));   // bank = lane
@@ -235,7 +237,7 @@ __device__ __forceinline__ void tma_dec_step(uint32_t& x, uint32_t& cur, uint32_
             if (via_tex) e = tex1Dfetch<unsigned int>(tex, static_cast<int>(slot));
             else e = lds_u32_ro(tab + slot * 4);
         }
-        if (P::kWideMul) {
+        if (P::kWideMul & 2) {
             uint32_t lo;
             mul_wide_u32(e, 1u << 12, lo, f);                                  // f = e >> 20, lo = e << 12
             b = lo >> 20;
@@ -453,7 +455,7 @@ word_decode_tma_kernel(const uint8_t* __restrict__ blob, uint64_t blob_size, con
 
 // The configuration the C-ABI launches (tools/decode_lab.cu measures the alternatives; profiles/r2_decode_lab.md):
 // 2 CTAs of 32 warps per SM, fill check / ring wrap every 8 steps, ring of 4 x 512 B filled by cp.async (LDGSTS),
-// table by one TMA bulk copy, IMAD.WIDE field extraction.
-using DecShip = DecPolicy<32, 2, 8, kRefillCpAsync, 9, true, 0, 0, false>;
+// table by one TMA bulk copy, shift/mask field extraction.
+using DecShip = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 0, 0, 0, false>;
 
 }  // namespace rb200

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == bound, f"header/binding mismatch: {declared ^ bound}"
     for name in declared:
         assert hasattr(lib.dll, name), name
-    assert lib.dll.rb200_version() == 1
+    assert lib.dll.rb200_version() == 2        # RB200_VERSION: 2 added the rb200_comm_* / rb200_gather_* entry points
     assert lib.dll.rb200_strerror(-4) == b"corrupt or truncated stream"
 
 

@@ -214,37 +214,41 @@ int main(int argc, char** argv)
         };
         vs.push_back(v);
     }
-    //                       warps, CTAs/SM, group, refill, log2(unit), wide-mul, tex-every, ablate, iadd3
-    using Tma512 = DecPolicy<32, 2, 8, kRefillTma, 9>;
-    using Tma1k20 = DecPolicy<20, 2, 8, kRefillTma, 10>;
-    using Cpa512 = DecPolicy<32, 2, 8, kRefillCpAsync, 9>;
-    using Cpa512i = DecPolicy<32, 2, 8, kRefillCpAsync, 9, true, 0, 0, true>;
-    using Cpa512g4 = DecPolicy<32, 2, 4, kRefillCpAsync, 9>;
-    using Cpa512w24 = DecPolicy<24, 2, 8, kRefillCpAsync, 9>;
-    using Cpa512w16x4 = DecPolicy<16, 4, 8, kRefillCpAsync, 9>;
-    using Cpa512w16x4i = DecPolicy<16, 4, 8, kRefillCpAsync, 9, true, 0, 0, true>;
-    using Cpa512s = DecPolicy<32, 2, 8, kRefillCpAsync, 9, false>;
-    using Cpa512si = DecPolicy<32, 2, 8, kRefillCpAsync, 9, false, 0, 0, true>;
-    using CpaT8 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, true, 8>;
-    using A1 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, true, 0, kAblGatherConflictFree>;
-    using A2 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, true, 0, kAblNoSymbolStore>;
-    using A4 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, true, 0, kAblNoRingRead>;
-    using A8 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, true, 0, kAblNoRefill>;
-    using A3 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, true, 0, kAblGatherConflictFree | kAblNoSymbolStore>;
-    using A9 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, true, 0, kAblGatherConflictFree | kAblNoRefill>;
-    using A15 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, true, 0, 15>;
-    vs.push_back(tma_variant<Cpa512>("cpa512_w32x2", "persistent; ring of 4 x 512 B filled by cp.async 16 B/lane (LDGSTS); 64 warps/SM"));
-    vs.push_back(tma_variant<Cpa512i>("cpa512_w32x2_iadd3", "same, refill address and cursor update on the ALU pipe (IADD3) instead of IMAD"));
-    vs.push_back(tma_variant<Cpa512g4>("cpa512_w32x2_g4", "same, fill check every 4 steps"));
-    vs.push_back(tma_variant<Cpa512w24>("cpa512_w24x2", "same, 48 warps/SM"));
-    vs.push_back(tma_variant<Cpa512w16x4>("cpa512_w16x4", "same, CTAs of 16 warps"));
-    vs.push_back(tma_variant<Cpa512w16x4i>("cpa512_w16x4_iadd3"));
-    vs.push_back(tma_variant<Cpa512s>("cpa512_w32x2_shifts", "field extraction with SHF/LOP3 instead of IMAD.WIDE"));
-    vs.push_back(tma_variant<Cpa512si>("cpa512_w32x2_shifts_iadd3"));
-    vs.push_back(tma_variant<Tma512>("tma512_w32x2", "persistent; ring of 4 x 512 B filled by cp.async.bulk (TMA) + mbarrier; 64 warps/SM"));
+    //                       warps, CTAs/SM, group, refill, log2(unit), wide-mul (1 state, 2 entry), tex-every, ablate, iadd3
+    using Ship = DecShip;
+    using Tma512 = DecPolicy<32, 2, 8, kRefillTma, 9, 0>;
+    using Tma1k20 = DecPolicy<20, 2, 8, kRefillTma, 10, 0>;
+    using CpaW3 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 3>;
+    using CpaW1 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 1>;
+    using CpaW2 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 2>;
+    using CpaI = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 0, 0, 0, true>;
+    using CpaG4 = DecPolicy<32, 2, 4, kRefillCpAsync, 9, 0>;
+    using CpaW24 = DecPolicy<24, 2, 8, kRefillCpAsync, 9, 0>;
+    using CpaW16x4 = DecPolicy<16, 4, 8, kRefillCpAsync, 9, 0>;
+    using Cpa1k20 = DecPolicy<20, 2, 8, kRefillCpAsync, 10, 0>;
+    using CpaT8 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 0, 8>;
+    using CpaT4 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 0, 4>;
+    using A1 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 0, 0, kAblGatherConflictFree>;
+    using A2 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 0, 0, kAblNoSymbolStore>;
+    using A4 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 0, 0, kAblNoRingRead>;
+    using A8 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 0, 0, kAblNoRefill>;
+    using A3 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 0, 0, kAblGatherConflictFree | kAblNoSymbolStore>;
+    using A9 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 0, 0, kAblGatherConflictFree | kAblNoRefill>;
+    using A15 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 0, 0, 15>;
+    vs.push_back(tma_variant<Ship>("ship", "SHIPPED: persistent, 2 x 32 warps/SM, TMA-staged table, ring of 4 x 512 B by cp.async (LDGSTS), shift/mask extraction"));
+    vs.push_back(tma_variant<CpaW3>("ship_wide_both", "field extraction by two IMAD.WIDE (16 instead of 18 instructions per step)"));
+    vs.push_back(tma_variant<CpaW1>("ship_wide_state", "IMAD.WIDE for x >> 12 / slot address only"));
+    vs.push_back(tma_variant<CpaW2>("ship_wide_entry", "IMAD.WIDE for freq / bias only"));
+    vs.push_back(tma_variant<CpaI>("ship_iadd3", "refill address and cursor update on the ALU pipe (IADD3) instead of IMAD"));
+    vs.push_back(tma_variant<CpaG4>("ship_g4", "fill check / ring wrap every 4 steps instead of 8"));
+    vs.push_back(tma_variant<CpaW24>("ship_w24x2", "48 warps/SM"));
+    vs.push_back(tma_variant<CpaW16x4>("ship_w16x4", "CTAs of 16 warps"));
+    vs.push_back(tma_variant<Cpa1k20>("ship_1k_w20x2", "ring of 4 x 1 KiB; 40 warps/SM"));
+    vs.push_back(tma_variant<Tma512>("tma512_w32x2", "ring filled by cp.async.bulk (TMA) + one mbarrier per slot instead of LDGSTS"));
     vs.push_back(tma_variant<Tma1k20>("tma1k_w20x2", "ring of 4 x 1 KiB by TMA; 40 warps/SM"));
-    vs.push_back(tma_variant<CpaT8>("cpa512_tex_every8", "every 8th table gather through the TEX pipe (tex1Dfetch)"));
-    vs.push_back(tma_variant<A1>("abl_gather_conflict_free", "ABLATION on cpa512_w32x2: gather address forced to bank = lane (+1 IMAD)"));
+    vs.push_back(tma_variant<CpaT4>("tex_every4", "every 4th table gather through the TEX pipe (tex1Dfetch)"));
+    vs.push_back(tma_variant<CpaT8>("tex_every8", "every 8th table gather through the TEX pipe"));
+    vs.push_back(tma_variant<A1>("abl_gather_conflict_free", "ABLATION on ship: gather address forced to bank = lane"));
     vs.push_back(tma_variant<A2>("abl_no_symbol_store", "ABLATION: no STG.U8"));
     vs.push_back(tma_variant<A4>("abl_no_ring_read", "ABLATION: refill word = address, no LDS.U16"));
     vs.push_back(tma_variant<A8>("abl_no_refill", "ABLATION: no ring refills / waits (blob never read)"));
@@ -252,8 +256,8 @@ int main(int argc, char** argv)
     vs.push_back(tma_variant<A9>("abl_cf_gather_no_refill"));
     vs.push_back(tma_variant<A15>("abl_all", "ABLATION: all four -- what the ALU/issue side alone costs"));
     if (only.empty()) {
-        describe<Tma512>("tma512_w32x2"); describe<Cpa512>("cpa512_w32x2"); describe<Cpa512i>("cpa512_w32x2_iadd3");
-        describe<Cpa512w24>("cpa512_w24x2"); describe<Cpa512w16x4>("cpa512_w16x4");
+        describe<Ship>("ship"); describe<CpaW3>("ship_wide_both"); describe<Tma512>("tma512_w32x2");
+        describe<CpaW24>("ship_w24x2"); describe<CpaW16x4>("ship_w16x4");
     }
 
     cudaEvent_t e0, e1;
