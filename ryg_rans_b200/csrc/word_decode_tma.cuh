@@ -455,7 +455,7 @@ word_decode_tma_kernel(const uint8_t* __restrict__ blob, uint64_t blob_size, con
 
 // The configuration the C-ABI launches (tools/decode_lab.cu measures the alternatives; profiles/r2_decode_lab.md):
 // 2 CTAs of 32 warps per SM, fill check / ring wrap every 8 steps, ring of 4 x 512 B filled by cp.async (LDGSTS),
-// table by one TMA bulk copy, shift/mask field extraction.
-using DecShip = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 0, 0, 0, false>;
+// table by one TMA bulk copy, freq / bias by one IMAD.WIDE, slot and x >> 12 by shift / mask.
+using DecShip = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 2, 0, 0, false>;
 
 }  // namespace rb200

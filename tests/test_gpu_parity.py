@@ -64,6 +64,33 @@ def test_word_reference_stream_n32(gpu_ctx, oracle_lib, ref_lib, gen):
     assert np.array_equal(dec, data) and used == ref_stream.size
 
 
+def test_book1_known_answer_through_the_gpu(gpu_ctx, oracle_lib):
+    """The reference-held known answer, through the GPU: the reference's own 32-way word-coder stream of
+    book1 is 435 702 bytes (tests/golden/book1_n32.npz, made by make_book1_stream.py from the reference's primitives).
+    The GPU decodes it -- the bytes must hash to book1's SHA-256 -- and re-encoding them as ONE chunk must reproduce
+    the stream byte for byte; the oracle agrees on both."""
+    import hashlib
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "book1_n32.npz"))
+    stream, freqs, n = g["stream"], g["freqs"], int(g["n"])
+    assert stream.size == 435702 and n == 768771
+    chunk = 1 << 20                                   # one chunk >= n: the container is exactly one reference stream
+    gap = (-stream.size) % 16                         # streams are END-aligned to 16 bytes inside a blob
+    blob = np.concatenate([np.zeros(gap, np.uint8), stream])
+    offs = np.array([gap, blob.size], np.uint64)
+    model = gpu_ctx.model(WORD, 12, freqs)
+    book = gpu_ctx.decode_host(model, blob, offs, n, chunk)
+    assert hashlib.sha256(book.tobytes()).digest() == g["book_sha256"].tobytes()          # "decode ok!"
+    assert hashlib.sha256(book.tobytes()).hexdigest() == "9ffa47cd93bccd732f20e0c304203cfbc1b8a91bedac536e2d8f6051003d9951"
+    f2, cum = oracle_lib.model(book, 12)
+    assert np.array_equal(f2, freqs)                                                     # normalize_freqs(4096) of book1
+    gblob, goffs = gpu_ctx.encode_host(model, book, chunk)
+    assert gblob.size - int(goffs[0]) == 435702
+    assert np.array_equal(gblob[int(goffs[0]):], stream)
+    assert np.array_equal(oracle_lib.encode(orc.CODER_WORD, book, freqs, cum, 32), stream)
+    model.close()
+
+
 def test_word_corrupt_stream_is_reported(gpu_ctx, oracle_lib, gen):
     import ryg_rans_b200 as rb
     data = gen("zipf", 20000, 3)
@@ -518,6 +545,23 @@ def test_full_size_roundtrip_properties(gpu_ctx, coder, sb, kind):
     gpu_ctx.decode_device(model, blob.data_ptr(), size, offsets.data_ptr(), chunk, out.data_ptr(), n)
     gpu_ctx.sync()
     assert torch.equal(out, data)
+    # a sample of the 131 072 chunk streams against the oracle, byte for byte: first, last, the chunks either side of
+    # every 2^32-byte boundary the blob crosses (none at 1 GiB, but the indexing is 64-bit clean) and 64 random ones
+    import oracle as orc_mod
+    oracle_lib = orc_mod.Oracle()
+    freqs = st.freqs.copy()
+    cum = np.concatenate([[0], np.cumsum(freqs)]).astype(np.uint32)
+    offs_h = offsets.cpu().numpy().astype(np.uint64)
+    rng = np.random.default_rng(99)
+    picks = sorted(set([0, 1, n_chunks // 2, n_chunks - 2, n_chunks - 1] + [int(c) for c in rng.integers(0, n_chunks, 64)]))
+    ocoder = {WORD: orc_mod.CODER_WORD, ALIAS: orc_mod.CODER_ALIAS}[coder]
+    for c in picks:
+        lo, hi = c * chunk, min(n, (c + 1) * chunk)
+        sym = data[lo:hi].cpu().numpy()
+        want = oracle_lib.encode(ocoder, sym, freqs, cum, 32, sb)
+        b0, b1 = int(offs_h[c]), int(offs_h[c + 1]) & ~15
+        got = blob[b0:b1].cpu().numpy()
+        assert got.size == want.size and np.array_equal(got, want), f"chunk {c}: GPU stream != oracle stream"
     # corrupt one stream in the middle of the blob
     mid = int(offsets[n_chunks // 2]) + 200
     blob[mid:mid + 64] ^= 0x3C

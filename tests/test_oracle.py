@@ -108,6 +108,23 @@ def test_chunked_container_rules(oracle_lib, gen):
     assert np.array_equal(oracle_lib.chunked_decode(orc.CODER_WORD, blob, offs, data.size, f, c, 4096), data)
 
 
+def test_book1_n32_golden_stream(oracle_lib):
+    """tests/golden/book1_n32.npz is the reference's own 32-way word-coder stream of book1 (435 702 bytes, SURVEY 8a;
+    made by make_book1_stream.py).  The C restatement decodes it to bytes with book1's SHA-256 and re-encodes them to
+    the identical stream -- the same known answer the GPU test checks through the C-ABI."""
+    import hashlib
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "book1_n32.npz"))
+    stream, freqs, n = g["stream"], g["freqs"], int(g["n"])
+    assert stream.size == 435702 and n == 768771
+    cum = np.concatenate([[0], np.cumsum(freqs)]).astype(np.uint32)
+    book, used = oracle_lib.decode(orc.CODER_WORD, stream, n, freqs, cum, 32)
+    assert used == stream.size
+    assert hashlib.sha256(book.tobytes()).hexdigest() == "9ffa47cd93bccd732f20e0c304203cfbc1b8a91bedac536e2d8f6051003d9951"
+    f2, c2 = oracle_lib.model(book, 12)
+    assert np.array_equal(f2, freqs) and np.array_equal(c2, cum)
+    assert np.array_equal(oracle_lib.encode(orc.CODER_WORD, book, freqs, cum, 32), stream)
+
+
 # ---------------------------------------------------------------- needs /root/reference
 
 needs_reference = pytest.mark.skipif(not os.path.exists("/root/reference/book1"), reason="reference checkout not present")

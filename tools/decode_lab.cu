@@ -216,29 +216,29 @@ int main(int argc, char** argv)
     }
     //                       warps, CTAs/SM, group, refill, log2(unit), wide-mul (1 state, 2 entry), tex-every, ablate, iadd3
     using Ship = DecShip;
-    using Tma512 = DecPolicy<32, 2, 8, kRefillTma, 9, 0>;
-    using Tma1k20 = DecPolicy<20, 2, 8, kRefillTma, 10, 0>;
+    using Tma512 = DecPolicy<32, 2, 8, kRefillTma, 9, 2>;
+    using Tma1k20 = DecPolicy<20, 2, 8, kRefillTma, 10, 2>;
     using CpaW3 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 3>;
     using CpaW1 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 1>;
-    using CpaW2 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 2>;
-    using CpaI = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 0, 0, 0, true>;
-    using CpaG4 = DecPolicy<32, 2, 4, kRefillCpAsync, 9, 0>;
-    using CpaW24 = DecPolicy<24, 2, 8, kRefillCpAsync, 9, 0>;
-    using CpaW16x4 = DecPolicy<16, 4, 8, kRefillCpAsync, 9, 0>;
-    using Cpa1k20 = DecPolicy<20, 2, 8, kRefillCpAsync, 10, 0>;
-    using CpaT8 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 0, 8>;
-    using CpaT4 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 0, 4>;
-    using A1 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 0, 0, kAblGatherConflictFree>;
-    using A2 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 0, 0, kAblNoSymbolStore>;
-    using A4 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 0, 0, kAblNoRingRead>;
-    using A8 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 0, 0, kAblNoRefill>;
-    using A3 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 0, 0, kAblGatherConflictFree | kAblNoSymbolStore>;
-    using A9 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 0, 0, kAblGatherConflictFree | kAblNoRefill>;
-    using A15 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 0, 0, 15>;
-    vs.push_back(tma_variant<Ship>("ship", "SHIPPED: persistent, 2 x 32 warps/SM, TMA-staged table, ring of 4 x 512 B by cp.async (LDGSTS), shift/mask extraction"));
+    using CpaW0 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 0>;
+    using CpaI = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 2, 0, 0, true>;
+    using CpaG4 = DecPolicy<32, 2, 4, kRefillCpAsync, 9, 2>;
+    using CpaW24 = DecPolicy<24, 2, 8, kRefillCpAsync, 9, 2>;
+    using CpaW16x4 = DecPolicy<16, 4, 8, kRefillCpAsync, 9, 2>;
+    using Cpa1k20 = DecPolicy<20, 2, 8, kRefillCpAsync, 10, 2>;
+    using CpaT8 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 2, 8>;
+    using CpaT4 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 2, 4>;
+    using A1 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 2, 0, kAblGatherConflictFree>;
+    using A2 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 2, 0, kAblNoSymbolStore>;
+    using A4 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 2, 0, kAblNoRingRead>;
+    using A8 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 2, 0, kAblNoRefill>;
+    using A3 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 2, 0, kAblGatherConflictFree | kAblNoSymbolStore>;
+    using A9 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 2, 0, kAblGatherConflictFree | kAblNoRefill>;
+    using A15 = DecPolicy<32, 2, 8, kRefillCpAsync, 9, 2, 0, 15>;
+    vs.push_back(tma_variant<Ship>("ship", "SHIPPED: persistent, 2 x 32 warps/SM, TMA-staged table, ring of 4 x 512 B by cp.async (LDGSTS), freq/bias by one IMAD.WIDE"));
     vs.push_back(tma_variant<CpaW3>("ship_wide_both", "field extraction by two IMAD.WIDE (16 instead of 18 instructions per step)"));
     vs.push_back(tma_variant<CpaW1>("ship_wide_state", "IMAD.WIDE for x >> 12 / slot address only"));
-    vs.push_back(tma_variant<CpaW2>("ship_wide_entry", "IMAD.WIDE for freq / bias only"));
+    vs.push_back(tma_variant<CpaW0>("ship_shifts_only", "no IMAD.WIDE: every field by shift / mask (18 instructions per step)"));
     vs.push_back(tma_variant<CpaI>("ship_iadd3", "refill address and cursor update on the ALU pipe (IADD3) instead of IMAD"));
     vs.push_back(tma_variant<CpaG4>("ship_g4", "fill check / ring wrap every 4 steps instead of 8"));
     vs.push_back(tma_variant<CpaW24>("ship_w24x2", "48 warps/SM"));
