@@ -342,10 +342,9 @@ def measure(rig, workload, n, chunk, steps, warmup, e2e_steps, headline):
         bfreqs = torch.zeros(n_blocks * 256, dtype=torch.int16, device=dev)
         model_bytes = 512 * n_blocks                  # the per-block frequency tables travel with the blob
 
-        def enc():                                    # per-block models are part of encoding a block
-            ctx.blocks_build_models_device(data.data_ptr(), n_blocks, BLOCK_SIZE, bfreqs.data_ptr())
-            ctx.blocks_encode_device(data.data_ptr(), n_blocks, BLOCK_SIZE, bfreqs.data_ptr(), chunk, blob.data_ptr(), cap,
-                                     offsets.data_ptr())
+        def enc():                                    # per-block models are part of encoding a block: one fused launch
+            ctx.blocks_model_encode_device(data.data_ptr(), n_blocks, BLOCK_SIZE, bfreqs.data_ptr(), chunk, blob.data_ptr(), cap,
+                                           offsets.data_ptr())
 
         def dec(blob_size):
             ctx.blocks_decode_device(blob.data_ptr(), blob_size, offsets.data_ptr(), bfreqs.data_ptr(), n_blocks, BLOCK_SIZE, chunk,
@@ -494,9 +493,8 @@ def measure_e2e(rig, workload, data, n, chunk, cap, n_chunks, model, coder, sb, 
 
     def step(with_model):
         if blocks:
-            lib.check(lib.dll.rb200_blocks_build_models(ctx.h, h_in.data_ptr(), n_blocks, BLOCK_SIZE, h_freqs.data_ptr(), rb.MEM_HOST), ctx.h)
-            lib.check(lib.dll.rb200_blocks_encode(ctx.h, h_in.data_ptr(), n_blocks, BLOCK_SIZE, h_freqs.data_ptr(), chunk,
-                                                  h_blob.data_ptr(), cap, h_off.ctypes.data, C.byref(size), rb.MEM_HOST), ctx.h)
+            lib.check(lib.dll.rb200_blocks_model_encode(ctx.h, h_in.data_ptr(), n_blocks, BLOCK_SIZE, h_freqs.data_ptr(), chunk,
+                                                        h_blob.data_ptr(), cap, h_off.ctypes.data, C.byref(size), rb.MEM_HOST), ctx.h)
             lib.check(lib.dll.rb200_blocks_decode(ctx.h, h_blob.data_ptr(), size.value, h_off.ctypes.data, h_freqs.data_ptr(),
                                                   n_blocks, BLOCK_SIZE, chunk, h_out.data_ptr(), rb.MEM_HOST), ctx.h)
             return
@@ -526,9 +524,9 @@ def measure_e2e(rig, workload, data, n, chunk, cap, n_chunks, model, coder, sb, 
         os.sched_setaffinity(0, saved_affinity)
     moved = int(n + size.value + 8 * (n_chunks + 1) + (512 * n_blocks if blocks else 0))
     res = {"value": rig.world * n * e2e_steps / dt / 1e9, "unit": UNIT, "host_numa_node": numa_node,
-           "h2d_bytes_per_step": moved + (int(n) if blocks else 0), "d2h_bytes_per_step": moved, "steps": e2e_steps,
+           "h2d_bytes_per_step": moved, "d2h_bytes_per_step": moved, "steps": e2e_steps,
            "pcie_gbs_per_direction_per_rank": moved * e2e_steps / dt / 1e9,
-           "note": ("rb200_blocks_build_models + rb200_blocks_encode + rb200_blocks_decode" if blocks else "rb200_encode + rb200_decode")
+           "note": ("rb200_blocks_model_encode + rb200_blocks_decode" if blocks else "rb200_encode + rb200_decode")
                    + " with RB200_MEM_HOST on pinned buffers, wall clock",
            "bound": "PCIe: each call streams its input in and its output back concurrently; with both directions busy the "
                     "slower one gets 43-47 GB/s on this box (tools/pcie_probe.py, profiles/r1_pcie_copies.log)"}

@@ -165,6 +165,14 @@ int rb200_blocks_encode(rb200_ctx* ctx, const uint8_t* in, uint32_t n_blocks, ui
 int rb200_blocks_decode(rb200_ctx* ctx, const uint8_t* blob, size_t blob_size, const uint64_t* offsets,
                         const uint16_t* block_freqs, uint32_t n_blocks, uint32_t block_size,
                         uint32_t chunk_syms, uint8_t* out, int mem_kind);
+/* rb200_blocks_build_models + rb200_blocks_encode in ONE launch: every block's model is built (count_freqs +
+ * normalize_freqs(4096), main.cpp:59-129, bit-exact) by the CTA that then encodes the block, and returned in
+ * block_freqs[n_blocks][256] -- what a decoder needs next to the blob.  A block has at most 32 chunks
+ * (block_size / chunk_syms <= 32: one warp per chunk, one CTA per block); HOST mode pipelines slices of whole blocks
+ * over three streams like rb200_encode. */
+int rb200_blocks_model_encode(rb200_ctx* ctx, const uint8_t* in, uint32_t n_blocks, uint32_t block_size,
+                              uint16_t* block_freqs, uint32_t chunk_syms,
+                              uint8_t* blob, size_t blob_cap, uint64_t* offsets, size_t* blob_size, int mem_kind);
 
 /* ---------------------------------------------------------------- multi-GPU: gathering the shards' blobs (NCCL) */
 

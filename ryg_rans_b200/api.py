@@ -43,6 +43,8 @@ EXPORTS = [
     ("rb200_blocks_build_models", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int]),
     ("rb200_blocks_encode", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p,
                                       C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t), C.c_int]),
+    ("rb200_blocks_model_encode", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p,
+                                            C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t), C.c_int]),
     ("rb200_blocks_decode", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
                                       C.c_uint32, C.c_void_p, C.c_int]),
     ("rb200_comm_unique_id", C.c_int, [C.c_void_p]),
@@ -264,6 +266,10 @@ class Context:
         self.lib.check(self.lib.dll.rb200_blocks_encode(self.h, in_ptr, n_blocks, block_size, freqs_ptr, chunk_syms, blob_ptr,
                                                         blob_cap, offsets_ptr, None, MEM_DEVICE), self.h)
 
+    def blocks_model_encode_device(self, in_ptr, n_blocks, block_size, freqs_ptr, chunk_syms, blob_ptr, blob_cap, offsets_ptr):
+        self.lib.check(self.lib.dll.rb200_blocks_model_encode(self.h, in_ptr, n_blocks, block_size, freqs_ptr, chunk_syms, blob_ptr,
+                                                              blob_cap, offsets_ptr, None, MEM_DEVICE), self.h)
+
     def blocks_decode_device(self, blob_ptr, blob_size, offsets_ptr, freqs_ptr, n_blocks, block_size, chunk_syms, out_ptr):
         self.lib.check(self.lib.dll.rb200_blocks_decode(self.h, blob_ptr, blob_size, offsets_ptr, freqs_ptr, n_blocks, block_size,
                                                         chunk_syms, out_ptr, MEM_DEVICE), self.h)
@@ -288,6 +294,19 @@ class Context:
                                                         chunk_syms, _np_ptr(blob), cap, _np_ptr(offsets), C.byref(size),
                                                         MEM_HOST), self.h)
         return blob[:size.value].copy(), offsets
+
+    def blocks_model_encode_host(self, data, n_blocks, block_size, chunk_syms):
+        """models + encode in one call; returns (blob, offsets, block_freqs)"""
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        freqs = np.zeros((n_blocks, 256), np.uint16)
+        n_chunks = n_blocks * (block_size // chunk_syms)
+        cap = self.encode_bound(data.size, chunk_syms)
+        blob = np.zeros(max(cap, 16), np.uint8)
+        offsets = np.zeros(n_chunks + 1, np.uint64)
+        size = C.c_size_t(0)
+        self.lib.check(self.lib.dll.rb200_blocks_model_encode(self.h, _np_ptr(data), n_blocks, block_size, _np_ptr(freqs), chunk_syms,
+                                                              _np_ptr(blob), cap, _np_ptr(offsets), C.byref(size), MEM_HOST), self.h)
+        return blob[:size.value].copy(), offsets, freqs
 
     def blocks_decode_host(self, blob, offsets, block_freqs, n_blocks, block_size, chunk_syms):
         blob = np.ascontiguousarray(blob, dtype=np.uint8)

@@ -29,10 +29,12 @@ constexpr uint32_t kAliasDecReplicas = 8;    // quarter-warp lanes hit 8 differe
 //           256 x {start | freq << 16} table.
 // then RansDecRenorm (rans_byte.h:307-318) for both.
 // FULL: all 32 lanes take part (active == true at compile time); only the ragged last step of a chunk does not.
-template <bool ALIAS, bool FULL>
+// SB: scale_bits as a compile-time constant (16, 14, 12: masks and shift counts become immediates), 0 = use `sb_rt`.
+template <bool ALIAS, bool FULL, uint32_t SB>
 __device__ __forceinline__ void alias_dec_step(uint32_t& x, uint32_t& cursor, uint32_t tab_lane, uint32_t ring, uint8_t* o,
-                                               uint32_t lt, uint32_t sb, bool active)
+                                               uint32_t lt, uint32_t sb_rt, bool active)
 {
+    const uint32_t sb = SB ? SB : sb_rt;
     bool n1 = false, n2 = false;
     if (active) {
         const uint32_t xm = x & ((1u << sb) - 1);                          // main_alias.cpp:258 / rans_byte.h:127
@@ -104,12 +106,13 @@ __device__ __forceinline__ void alias_dec_step(uint32_t& x, uint32_t& cursor, ui
 }
 
 // ALIAS: g_tab = 256 x AliasDecEntry.  !ALIAS: g_tab = cum2sym[1 << sb] followed by 256 x u32 {start | freq << 16}.
-template <bool ALIAS>
+template <bool ALIAS, uint32_t SB>
 __global__ void __launch_bounds__(kAliasDecWarps * 32, 4)
-alias_decode_kernel(const uint8_t* __restrict__ blob, uint64_t blob_size, const uint64_t* __restrict__ offsets, uint32_t sb,
+alias_decode_kernel(const uint8_t* __restrict__ blob, uint64_t blob_size, const uint64_t* __restrict__ offsets, uint32_t sb_rt,
                     const void* __restrict__ g_tab, uint8_t* __restrict__ out, uint64_t n, uint32_t chunk_syms,
                     uint32_t n_chunks, uint32_t* __restrict__ status)
 {
+    const uint32_t sb = SB ? SB : sb_rt;
     extern __shared__ __align__(1024) uint8_t s_adec[];       // [16 x 1 KiB rings][table]
     uint4* s_tab = reinterpret_cast<uint4*>(s_adec + kAliasDecWarps * kRingBytes);
     if (ALIAS) {
@@ -153,32 +156,32 @@ alias_decode_kernel(const uint8_t* __restrict__ blob, uint64_t blob_size, const 
     uint32_t g = 0;
     for (; g + 8 <= steps; g += 8) {
         win.top_up(cursor, lane);
-        alias_dec_step<ALIAS, true>(x, cursor, tab_lane, win.ring, o, lt, sb, true);
-        alias_dec_step<ALIAS, true>(x, cursor, tab_lane, win.ring, o + 32, lt, sb, true);
-        alias_dec_step<ALIAS, true>(x, cursor, tab_lane, win.ring, o + 64, lt, sb, true);
-        alias_dec_step<ALIAS, true>(x, cursor, tab_lane, win.ring, o + 96, lt, sb, true);
+        alias_dec_step<ALIAS, true, SB>(x, cursor, tab_lane, win.ring, o, lt, sb, true);
+        alias_dec_step<ALIAS, true, SB>(x, cursor, tab_lane, win.ring, o + 32, lt, sb, true);
+        alias_dec_step<ALIAS, true, SB>(x, cursor, tab_lane, win.ring, o + 64, lt, sb, true);
+        alias_dec_step<ALIAS, true, SB>(x, cursor, tab_lane, win.ring, o + 96, lt, sb, true);
         win.top_up(cursor, lane);
-        alias_dec_step<ALIAS, true>(x, cursor, tab_lane, win.ring, o + 128, lt, sb, true);
-        alias_dec_step<ALIAS, true>(x, cursor, tab_lane, win.ring, o + 160, lt, sb, true);
-        alias_dec_step<ALIAS, true>(x, cursor, tab_lane, win.ring, o + 192, lt, sb, true);
-        alias_dec_step<ALIAS, true>(x, cursor, tab_lane, win.ring, o + 224, lt, sb, true);
+        alias_dec_step<ALIAS, true, SB>(x, cursor, tab_lane, win.ring, o + 128, lt, sb, true);
+        alias_dec_step<ALIAS, true, SB>(x, cursor, tab_lane, win.ring, o + 160, lt, sb, true);
+        alias_dec_step<ALIAS, true, SB>(x, cursor, tab_lane, win.ring, o + 192, lt, sb, true);
+        alias_dec_step<ALIAS, true, SB>(x, cursor, tab_lane, win.ring, o + 224, lt, sb, true);
         o += 256;
     }
     if (g + 4 <= steps) {
         win.top_up(cursor, lane);
-        alias_dec_step<ALIAS, true>(x, cursor, tab_lane, win.ring, o, lt, sb, true);
-        alias_dec_step<ALIAS, true>(x, cursor, tab_lane, win.ring, o + 32, lt, sb, true);
-        alias_dec_step<ALIAS, true>(x, cursor, tab_lane, win.ring, o + 64, lt, sb, true);
-        alias_dec_step<ALIAS, true>(x, cursor, tab_lane, win.ring, o + 96, lt, sb, true);
+        alias_dec_step<ALIAS, true, SB>(x, cursor, tab_lane, win.ring, o, lt, sb, true);
+        alias_dec_step<ALIAS, true, SB>(x, cursor, tab_lane, win.ring, o + 32, lt, sb, true);
+        alias_dec_step<ALIAS, true, SB>(x, cursor, tab_lane, win.ring, o + 64, lt, sb, true);
+        alias_dec_step<ALIAS, true, SB>(x, cursor, tab_lane, win.ring, o + 96, lt, sb, true);
         o += 128;
         g += 4;
     }
     win.top_up(cursor, lane);
     for (; g < steps; g++) {
-        alias_dec_step<ALIAS, true>(x, cursor, tab_lane, win.ring, o, lt, sb, true);
+        alias_dec_step<ALIAS, true, SB>(x, cursor, tab_lane, win.ring, o, lt, sb, true);
         o += 32;
     }
-    if (rem) alias_dec_step<ALIAS, false>(x, cursor, tab_lane, win.ring, o, lt, sb, lane < rem);
+    if (rem) alias_dec_step<ALIAS, false, SB>(x, cursor, tab_lane, win.ring, o, lt, sb, lane < rem);
 
     const bool bad = (cursor != static_cast<uint32_t>(end)) || (x != kByteL);
     if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(status, kStatStream);
@@ -216,10 +219,11 @@ struct AliasEncState {
 //   !ALIAS: RansEncPutSymbol (rans_byte.h:258-280);   table {x_max, rcp_freq, bias, cmpl_freq | rcp_shift << 16}
 //           = RansEncSymbol (rans_byte.h:159-165), bit 31 of the last word marks a symbol outside the model
 // FULL: all 32 lanes take part (active == true at compile time); only the ragged first step of a chunk does not.
-template <bool ALIAS, bool FULL>
+template <bool ALIAS, bool FULL, uint32_t SB>
 __device__ __forceinline__ void alias_enc_step(AliasEncState& st, uint32_t sym, uint32_t tab_lane, uint32_t remap, uint32_t ring,
-                                               uint32_t gt, uint32_t sb, bool active)
+                                               uint32_t gt, uint32_t sb_rt, bool active)
 {
+    const uint32_t sb = SB ? SB : sb_rt;
     bool n1 = false, n2 = false;
     uint4 e = make_uint4(0, 1, 0, 0);
     uint32_t x_max = 0;
@@ -295,7 +299,7 @@ __device__ __forceinline__ void alias_enc_step(AliasEncState& st, uint32_t sym, 
 
 // Encode m symbols (one warp) as one 32-way byte-renormalised stream ending at slot_end (16-byte aligned);
 // returns the stream size in bytes (warp-uniform).
-template <bool ALIAS>
+template <bool ALIAS, uint32_t SB>
 __device__ __forceinline__ uint32_t alias_encode_stream(const uint8_t* __restrict__ chunk_in, uint32_t m, uint32_t tab, uint32_t remap,
                                                         uint32_t wsm, uint32_t sb, uint8_t* __restrict__ slot_end,
                                                         uint32_t* __restrict__ status)
@@ -319,11 +323,11 @@ __device__ __forceinline__ uint32_t alias_encode_stream(const uint8_t* __restric
     if (rem) {
         const bool active = lane < rem;
         const uint32_t s = active ? chunk_in[static_cast<uint64_t>(steps) * 32 + lane] : 0;
-        alias_enc_step<ALIAS, false>(st, s, tab_lane, remap, ring, gt, sb, active);
+        alias_enc_step<ALIAS, false, SB>(st, s, tab_lane, remap, ring, gt, sb, active);
     }
     for (uint32_t g = steps; g > nblk * 16; g--) {
         const uint32_t s = chunk_in[static_cast<uint64_t>(g - 1) * 32 + lane];
-        alias_enc_step<ALIAS, true>(st, s, tab_lane, remap, ring, gt, sb, true);
+        alias_enc_step<ALIAS, true, SB>(st, s, tab_lane, remap, ring, gt, sb, true);
         if (((g - 1) & 3) == 0) word_enc_flush(kEncRingBytes - 1 - st.wpos, flushed, ring, slot_end, lane);
     }
     word_enc_flush(kEncRingBytes - 1 - st.wpos, flushed, ring, slot_end, lane);
@@ -343,7 +347,7 @@ __device__ __forceinline__ uint32_t alias_encode_stream(const uint8_t* __restric
         for (int grp = 3; grp >= 0; grp--) {
 #pragma unroll
             for (int j = 3; j >= 0; j--)
-                alias_enc_step<ALIAS, true>(st, lds_u8(stage + (grp * 4 + j) * 32 + lane), tab_lane, remap, ring, gt, sb, true);
+                alias_enc_step<ALIAS, true, SB>(st, lds_u8(stage + (grp * 4 + j) * 32 + lane), tab_lane, remap, ring, gt, sb, true);
             if (kEncRingBytes - 1 - st.wpos - flushed >= 256) word_enc_flush(kEncRingBytes - 1 - st.wpos, flushed, ring, slot_end, lane);
         }
     }
@@ -372,14 +376,15 @@ __device__ __forceinline__ uint32_t alias_encode_stream(const uint8_t* __restric
 //                    sizes[] written for the tile scan + compaction that follow;
 //   look != nullptr: fused -- chunk ids from an atomic counter, two scratch slots per warp, warp 0 of CTA 0 is the
 //                    scanner, every worker places chunk k after encoding chunk k+1 (see word_kernels.cuh, K2f).
-template <bool ALIAS>
+template <bool ALIAS, uint32_t SB>
 __global__ void __launch_bounds__(kAliasEncWarps * 32, 1)
-alias_encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_syms, uint32_t n_chunks, uint32_t sb,
+alias_encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_syms, uint32_t n_chunks, uint32_t sb_rt,
                     const AliasEncEntry* __restrict__ g_enc, const uint16_t* __restrict__ g_remap,
                     uint8_t* __restrict__ scratch, uint32_t slot_bytes, uint32_t* __restrict__ sizes,
                     uint64_t* __restrict__ look, uint32_t* __restrict__ counter, uint8_t* __restrict__ blob, uint64_t blob_cap,
                     uint64_t* __restrict__ offsets, uint32_t* __restrict__ status)
 {
+    const uint32_t sb = SB ? SB : sb_rt;
     extern __shared__ __align__(1024) uint8_t s_alias[];      // [32 x 1.0 KiB stage+ring][32 KiB table][remap]
     uint4* s_tab = reinterpret_cast<uint4*>(s_alias + kAliasEncWarps * kEncWarpSmem);
     uint4* s_remap = reinterpret_cast<uint4*>(s_alias + kAliasEncFixedSmem);
@@ -402,7 +407,7 @@ alias_encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_s
         for (uint32_t chunk = blockIdx.x * kAliasEncWarps + warp; chunk < n_chunks; chunk += gridDim.x * kAliasEncWarps) {
             const uint64_t first = static_cast<uint64_t>(chunk) * chunk_syms;
             const uint32_t m = static_cast<uint32_t>(min(static_cast<uint64_t>(chunk_syms), n - first));
-            const uint32_t produced = alias_encode_stream<ALIAS>(in + first, m, tab, remap, wsm, sb,
+            const uint32_t produced = alias_encode_stream<ALIAS, SB>(in + first, m, tab, remap, wsm, sb,
                                                                  scratch + static_cast<uint64_t>(chunk + 1) * slot_bytes, status);
             if (lane == 0) sizes[chunk] = produced;
         }
@@ -422,7 +427,7 @@ alias_encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_s
         if (chunk >= n_chunks) break;
         const uint64_t first = static_cast<uint64_t>(chunk) * chunk_syms;
         const uint32_t m = static_cast<uint32_t>(min(static_cast<uint64_t>(chunk_syms), n - first));
-        const uint32_t produced = alias_encode_stream<ALIAS>(in + first, m, tab, remap, wsm, sb,
+        const uint32_t produced = alias_encode_stream<ALIAS, SB>(in + first, m, tab, remap, wsm, sb,
                                                              slots + (parity + 1) * static_cast<uint64_t>(slot_bytes), status);
         if (lane == 0) st_relaxed_u64(look + chunk, kLookAgg | ((produced + 15u) & ~15u));
         __syncwarp();
@@ -440,17 +445,31 @@ alias_encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_s
                     offsets, lane, status);
 }
 
+// scale_bits the kernels are specialised for (main_alias.cpp:276 uses 16, main.cpp:136 / main64.cpp:136 use 14, the word
+// coder's 12); every other value runs the generic instantiation (SB = 0).
+template <bool ALIAS, uint32_t SB>
+inline void configure_alias_pair()
+{
+    const uint32_t dec_smem = ALIAS ? kAliasDecSmem : kAliasDecWarps * kRingBytes + 1024 + (1u << 16);
+    cudaFuncSetAttribute(alias_decode_kernel<ALIAS, SB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(alias_decode_kernel<ALIAS, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_smem);
+    cudaFuncSetAttribute(alias_encode_kernel<ALIAS, SB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(alias_encode_kernel<ALIAS, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         kAliasEncFixedSmem + (ALIAS ? (2u << 16) : 0u));
+}
 inline void configure_alias_kernels()
 {
-    cudaFuncSetAttribute(alias_decode_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(alias_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAliasDecSmem);
-    cudaFuncSetAttribute(alias_decode_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(alias_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAliasDecWarps * kRingBytes + 1024 + (1u << 16));
-    cudaFuncSetAttribute(alias_encode_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(alias_encode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAliasEncFixedSmem + (2u << 16));
-    cudaFuncSetAttribute(alias_encode_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(alias_encode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAliasEncFixedSmem);
+    configure_alias_pair<true, 0>(); configure_alias_pair<true, 16>(); configure_alias_pair<true, 14>(); configure_alias_pair<true, 12>();
+    configure_alias_pair<false, 0>(); configure_alias_pair<false, 16>(); configure_alias_pair<false, 14>(); configure_alias_pair<false, 12>();
 }
+
+#define RB200_ALIAS_SB_DISPATCH(sb, CALL) \
+    switch (sb) {                        \
+    case 16: { constexpr uint32_t SB = 16; CALL; } break; \
+    case 14: { constexpr uint32_t SB = 14; CALL; } break; \
+    case 12: { constexpr uint32_t SB = 12; CALL; } break; \
+    default: { constexpr uint32_t SB = 0; CALL; } break;  \
+    }
 
 // remap == nullptr selects the rans_byte cum2sym coder.  look == nullptr: split mode (sizes[] out, one slot per
 // chunk); otherwise fused mode (two slots per resident warp; look/counter zeroed by the caller).
@@ -462,12 +481,13 @@ inline int launch_alias_encode(cudaStream_t stream, uint32_t sms, const uint8_t*
 {
     uint32_t grid = (n_chunks + (look ? 1 : 0) + kAliasEncWarps - 1) / kAliasEncWarps;
     if (grid > sms) grid = sms;                       // persistent: one CTA per SM
-    if (remap)
-        alias_encode_kernel<true><<<grid, kAliasEncWarps * 32, kAliasEncFixedSmem + (2u << sb), stream>>>(
-            d_in, n, chunk_syms, n_chunks, sb, enc, remap, scratch, slot, sizes, look, counter, blob, blob_cap, offsets, status);
-    else
-        alias_encode_kernel<false><<<grid, kAliasEncWarps * 32, kAliasEncFixedSmem, stream>>>(
-            d_in, n, chunk_syms, n_chunks, sb, enc, nullptr, scratch, slot, sizes, look, counter, blob, blob_cap, offsets, status);
+    if (remap) {
+        RB200_ALIAS_SB_DISPATCH(sb, (alias_encode_kernel<true, SB><<<grid, kAliasEncWarps * 32, kAliasEncFixedSmem + (2u << sb), stream>>>(
+            d_in, n, chunk_syms, n_chunks, sb, enc, remap, scratch, slot, sizes, look, counter, blob, blob_cap, offsets, status)))
+    } else {
+        RB200_ALIAS_SB_DISPATCH(sb, (alias_encode_kernel<false, SB><<<grid, kAliasEncWarps * 32, kAliasEncFixedSmem, stream>>>(
+            d_in, n, chunk_syms, n_chunks, sb, enc, nullptr, scratch, slot, sizes, look, counter, blob, blob_cap, offsets, status)))
+    }
     return 0;
 }
 inline uint32_t alias_fused_slots(uint32_t sms) { return sms * kAliasEncWarps * 2; }
@@ -477,8 +497,8 @@ inline int launch_alias_decode(cudaStream_t stream, const uint8_t* blob, uint64_
                                uint32_t* status)
 {
     const uint32_t grid = (n_chunks + kAliasDecWarps - 1) / kAliasDecWarps;
-    alias_decode_kernel<true><<<grid, kAliasDecWarps * 32, kAliasDecSmem, stream>>>(blob, blob_size, offsets, sb, dec, out, n, chunk_syms,
-                                                                                    n_chunks, status);
+    RB200_ALIAS_SB_DISPATCH(sb, (alias_decode_kernel<true, SB><<<grid, kAliasDecWarps * 32, kAliasDecSmem, stream>>>(
+        blob, blob_size, offsets, sb, dec, out, n, chunk_syms, n_chunks, status)))
     return 0;
 }
 
@@ -487,8 +507,8 @@ inline int launch_byte_decode(cudaStream_t stream, const uint8_t* blob, uint64_t
                               const uint8_t* table, uint8_t* out, uint64_t n, uint32_t chunk_syms, uint32_t n_chunks, uint32_t* status)
 {
     const uint32_t grid = (n_chunks + kAliasDecWarps - 1) / kAliasDecWarps;
-    alias_decode_kernel<false><<<grid, kAliasDecWarps * 32, kAliasDecWarps * kRingBytes + 1024 + (1u << sb), stream>>>(
-        blob, blob_size, offsets, sb, table, out, n, chunk_syms, n_chunks, status);
+    RB200_ALIAS_SB_DISPATCH(sb, (alias_decode_kernel<false, SB><<<grid, kAliasDecWarps * 32, kAliasDecWarps * kRingBytes + 1024 + (1u << sb), stream>>>(
+        blob, blob_size, offsets, sb, table, out, n, chunk_syms, n_chunks, status)))
     return 0;
 }
 

@@ -76,21 +76,23 @@ inline void launch_histogram(cudaStream_t stream, const uint8_t* d_in, uint64_t 
 // ---------------------------------------------------------------------------
 constexpr int kModelWarps = 8;
 
-__global__ void __launch_bounds__(kModelWarps * 32)
-block_model_kernel(const uint8_t* __restrict__ in, uint32_t block_size, uint16_t* __restrict__ block_freqs,
-                   uint32_t* __restrict__ status)
-{
-    // one private histogram per warp (more copies per warp were measured slower: the copies share banks)
-    __shared__ __align__(16) uint32_t s_h[kModelWarps][256];
-    __shared__ uint32_t s_cnt[256];
-    __shared__ uint32_t s_cum[257];
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint8_t* blk = in + static_cast<uint64_t>(blockIdx.x) * block_size;
+// Shared-memory workspace of the per-block model build.
+struct BlockModelSmem {
+    uint32_t h[kModelWarps][256];     // one private histogram per (warp & 7); h[0] is reused for the 256 widths
+    uint32_t cnt[256];
+    uint32_t cum[257];
+};
 
-    for (uint32_t i = tid; i < kModelWarps * 256; i += blockDim.x) (&s_h[0][0])[i] = 0;
+// count_freqs + calc_cum_freqs + normalize_freqs(4096) (main.cpp:59-129) of one block by the whole CTA, bit-exact.
+// The CTA must call it convergently; on return (after a CTA barrier) dst[0..256) holds the normalised frequencies.
+__device__ __forceinline__ void block_model_build(const uint8_t* __restrict__ blk, uint32_t block_size, BlockModelSmem& sm,
+                                                  uint16_t* __restrict__ dst, uint32_t* __restrict__ status)
+{
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint32_t i = tid; i < kModelWarps * 256; i += blockDim.x) (&sm.h[0][0])[i] = 0;
     __syncthreads();
-    {   // count_freqs, main.cpp:59-66
-        uint32_t* h = s_h[warp];
+    {   // count_freqs, main.cpp:59-66 (more copies per warp were measured slower: the copies share banks)
+        uint32_t* h = sm.h[warp & (kModelWarps - 1)];
         const uint32_t head = min(block_size, static_cast<uint32_t>((16 - (reinterpret_cast<uintptr_t>(blk) & 15)) & 15));
         const uint32_t nvec = (block_size - head) / 16;
         const uint4* body = reinterpret_cast<const uint4*>(blk + head);
@@ -112,64 +114,73 @@ block_model_kernel(const uint8_t* __restrict__ in, uint32_t block_size, uint16_t
     for (uint32_t s = tid; s < 256; s += blockDim.x) {
         uint32_t t = 0;
 #pragma unroll
-        for (int w = 0; w < kModelWarps; w++) t += s_h[w][s];
-        s_cnt[s] = t;
+        for (int w = 0; w < kModelWarps; w++) t += sm.h[w][s];
+        sm.cnt[s] = t;
     }
     __syncthreads();
-    if (warp != 0) return;
-
-    // calc_cum_freqs (main.cpp:68-73): lane l owns symbols 8l .. 8l+7
-    uint32_t run = 0, local[8];
+    if (warp == 0) {
+        // calc_cum_freqs (main.cpp:68-73): lane l owns symbols 8l .. 8l+7
+        uint32_t run = 0, local[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) { local[j] = run; run += s_cnt[8 * lane + j]; }
-    uint32_t incl = run;
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= static_cast<uint32_t>(d)) incl += v;
-    }
-    const uint32_t base = incl - run;
-    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);      // == block_size
-    // resample, main.cpp:83-84 (cum[0] stays 0)
-#pragma unroll
-    for (int j = 0; j < 8; j++)
-        s_cum[8 * lane + j] = static_cast<uint32_t>((static_cast<uint64_t>(kWordSlots) * (base + local[j])) / total);
-    if (lane == 31) s_cum[256] = kWordSlots;                        // 4096 * total / total
-    __syncwarp();
-
-    // main.cpp:90-116, symbols in order.  Moving the boundaries between donor and taker by one changes exactly
-    // two widths (donor - 1, taker + 1), so the loop runs on widths; the arg-min over 256 widths is warp-wide
-    // with the key (width << 8 | symbol): lowest width first, lowest symbol on ties, as the reference's scan.
-    uint32_t* s_w = s_h[0];                                         // reuse: 256 widths
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-        const uint32_t t = 8 * lane + j;
-        s_w[t] = s_cum[t + 1] - s_cum[t];
-    }
-    __syncwarp();
-    bool failed = false;
-    for (uint32_t s = 0; s < 256; s++) {
-        if (s_cnt[s] == 0 || s_w[s] != 0) continue;                 // warp-uniform
-        uint32_t key = 0xffffffffu;
-        const uint4 lo = *reinterpret_cast<const uint4*>(&s_w[8 * lane]);
-        const uint4 hi = *reinterpret_cast<const uint4*>(&s_w[8 * lane + 4]);
-        const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        for (int j = 0; j < 8; j++) { local[j] = run; run += sm.cnt[8 * lane + j]; }
+        uint32_t incl = run;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= static_cast<uint32_t>(d)) incl += v;
+        }
+        const uint32_t base = incl - run;
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);      // == block_size
+        // resample, main.cpp:83-84 (cum[0] stays 0)
 #pragma unroll
         for (int j = 0; j < 8; j++)
-            if (w[j] > 1) key = min(key, (w[j] << 8) | (8 * lane + j));
-        key = __reduce_min_sync(0xffffffffu, key);
-        if (key == 0xffffffffu) { failed = true; break; }           // main.cpp:104
+            sm.cum[8 * lane + j] = static_cast<uint32_t>((static_cast<uint64_t>(kWordSlots) * (base + local[j])) / total);
+        if (lane == 31) sm.cum[256] = kWordSlots;                       // 4096 * total / total
         __syncwarp();
-        if (lane == 0) {
-            s_w[key & 0xffu] -= 1;                                  // main.cpp:107-113 in terms of widths
-            s_w[s] += 1;
+
+        // main.cpp:90-116, symbols in order.  Moving the boundaries between donor and taker by one changes exactly
+        // two widths (donor - 1, taker + 1), so the loop runs on widths; the arg-min over 256 widths is warp-wide
+        // with the key (width << 8 | symbol): lowest width first, lowest symbol on ties, as the reference's scan.
+        uint32_t* s_w = sm.h[0];                                        // reuse: 256 widths
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint32_t t = 8 * lane + j;
+            s_w[t] = sm.cum[t + 1] - sm.cum[t];
         }
         __syncwarp();
-    }
-    if (failed && lane == 0) atomicOr(status, kStatStream);
-    uint16_t* dst = block_freqs + static_cast<uint64_t>(blockIdx.x) * 256;
+        bool failed = false;
+        for (uint32_t s = 0; s < 256; s++) {
+            if (sm.cnt[s] == 0 || s_w[s] != 0) continue;                // warp-uniform
+            uint32_t key = 0xffffffffu;
+            const uint4 lo = *reinterpret_cast<const uint4*>(&s_w[8 * lane]);
+            const uint4 hi = *reinterpret_cast<const uint4*>(&s_w[8 * lane + 4]);
+            const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
-    for (int j = 0; j < 8; j++) dst[8 * lane + j] = static_cast<uint16_t>(s_w[8 * lane + j]);     // main.cpp:127
+            for (int j = 0; j < 8; j++)
+                if (w[j] > 1) key = min(key, (w[j] << 8) | (8 * lane + j));
+            key = __reduce_min_sync(0xffffffffu, key);
+            if (key == 0xffffffffu) { failed = true; break; }           // main.cpp:104
+            __syncwarp();
+            if (lane == 0) {
+                s_w[key & 0xffu] -= 1;                                  // main.cpp:107-113 in terms of widths
+                s_w[s] += 1;
+            }
+            __syncwarp();
+        }
+        if (failed && lane == 0) atomicOr(status, kStatStream);
+#pragma unroll
+        for (int j = 0; j < 8; j++) dst[8 * lane + j] = static_cast<uint16_t>(s_w[8 * lane + j]);     // main.cpp:127
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kModelWarps * 32)
+block_model_kernel(const uint8_t* __restrict__ in, uint32_t block_size, uint16_t* __restrict__ block_freqs,
+                   uint32_t* __restrict__ status)
+{
+    __shared__ __align__(16) BlockModelSmem sm;
+    block_model_build(in + static_cast<uint64_t>(blockIdx.x) * block_size, block_size, sm,
+                      block_freqs + static_cast<uint64_t>(blockIdx.x) * 256, status);
 }
 
 inline void launch_block_models(cudaStream_t stream, const uint8_t* d_in, uint32_t n_blocks, uint32_t block_size,
@@ -183,8 +194,10 @@ inline void launch_block_models(cudaStream_t stream, const uint8_t* d_in, uint32
 // ---------------------------------------------------------------------------
 constexpr int kMaxBlockWarps = 32;
 
-// cum[s] for the block's u16 frequencies; returns false if they do not sum to 4096
-__device__ __forceinline__ bool block_prefix(const uint16_t* __restrict__ freqs, uint32_t* s_cum, uint32_t* s_bad)
+// cum[s] for the block's frequencies (u16 from global memory, or the u32 widths the model build left in shared
+// memory); returns false if they do not sum to 4096
+template <class F>
+__device__ __forceinline__ bool block_prefix(const F* freqs, uint32_t* s_cum, uint32_t* s_bad)
 {
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     if (tid == 0) *s_bad = 0;
@@ -258,20 +271,12 @@ block_decode_kernel(const uint8_t* __restrict__ blob, uint64_t blob_size, const 
         word_decode_chunk<false>(blob, blob_size, offsets, chunk, smem_addr_pinned(s_tab), ring, dst, chunk_syms, status);
 }
 
-__global__ void __launch_bounds__(kMaxBlockWarps * 32)
-block_encode_kernel(const uint8_t* __restrict__ in, uint32_t block_size, const uint16_t* __restrict__ block_freqs,
-                    uint32_t chunk_syms, uint8_t* __restrict__ scratch, uint32_t slot_bytes, uint32_t* __restrict__ sizes,
-                    uint32_t* __restrict__ status)
+// The block's encoder table (8x replicated {magic, x_max | shift, start, 4096 - freq}) from its cumulative table in
+// s_cum; returns whether the 32-bit reciprocal is exact for every symbol of this model (tables.h: enc32), which
+// selects the kernel variant for the block.  Ends with a CTA barrier.
+__device__ __forceinline__ bool block_build_enc_table(const uint32_t* s_cum, bool ok, uint4* s_tab)
 {
-    extern __shared__ __align__(1024) uint8_t s_enc[];          // [32 KiB table][warps x 1 KiB stage + ring]
-    __shared__ uint32_t s_cum[257];
-    __shared__ uint32_t s_flag[1];
-    uint4* s_tab = reinterpret_cast<uint4*>(s_enc);
-    const uint32_t tid = threadIdx.x, warp = tid >> 5;
-    const uint16_t* freqs = block_freqs + static_cast<uint64_t>(blockIdx.x) * 256;
-    const uint32_t per_block = block_size / chunk_syms;
-    const bool ok = block_prefix(freqs, s_cum, &s_flag[0]);
-    // 32-bit reciprocal where it is exact for every symbol of this block's model (tables.h: enc32), else the 33-bit one
+    const uint32_t tid = threadIdx.x;
     bool exact32 = true;
     for (uint32_t s = tid; s < 256; s += blockDim.x) {
         const uint32_t f = ok ? s_cum[s + 1] - s_cum[s] : 0;
@@ -306,6 +311,23 @@ block_encode_kernel(const uint8_t* __restrict__ in, uint32_t block_size, const u
         for (uint32_t r = 0; r < kEncReplicas; r++) s_tab[s * kEncReplicas + r] = x;
     }
     __syncthreads();
+    return r32;
+}
+
+__global__ void __launch_bounds__(kMaxBlockWarps * 32)
+block_encode_kernel(const uint8_t* __restrict__ in, uint32_t block_size, const uint16_t* __restrict__ block_freqs,
+                    uint32_t chunk_syms, uint8_t* __restrict__ scratch, uint32_t slot_bytes, uint32_t* __restrict__ sizes,
+                    uint32_t* __restrict__ status)
+{
+    extern __shared__ __align__(1024) uint8_t s_enc[];          // [32 KiB table][warps x 1 KiB stage + ring]
+    __shared__ uint32_t s_cum[257];
+    __shared__ uint32_t s_flag[1];
+    uint4* s_tab = reinterpret_cast<uint4*>(s_enc);
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint16_t* freqs = block_freqs + static_cast<uint64_t>(blockIdx.x) * 256;
+    const uint32_t per_block = block_size / chunk_syms;
+    const bool ok = block_prefix(freqs, s_cum, &s_flag[0]);
+    const bool r32 = block_build_enc_table(s_cum, ok, s_tab);
     if (warp >= per_block) return;
     const uint32_t chunk = blockIdx.x * per_block + warp;
     const uint8_t* src = in + static_cast<uint64_t>(blockIdx.x) * block_size + static_cast<uint64_t>(warp) * chunk_syms;
@@ -314,6 +336,77 @@ block_encode_kernel(const uint8_t* __restrict__ in, uint32_t block_size, const u
         word_encode_chunk<true>(src, chunk_syms, chunk, smem_addr(s_enc), wsm, scratch, slot_bytes, sizes, status);
     else
         word_encode_chunk<false>(src, chunk_syms, chunk, smem_addr(s_enc), wsm, scratch, slot_bytes, sizes, status);
+}
+
+// K5f: per-block encode in ONE persistent launch -- model (optional), tables, encode, directory, placement.
+//
+// CTA 0 only hosts the scanner warp (word_kernels.cuh, K2f).  Every other CTA takes block ids from an atomic counter
+// (so chunks start in order), builds the block's model when BUILD (count_freqs + normalize_freqs, written to
+// block_freqs) or reads it, builds the encoder table in shared memory, and its warps encode the block's chunks into
+// per-warp scratch slots exactly as the fused word encoder does: publish the padded size, place the chunk of the
+// PREVIOUS block once the scanner has turned the published sizes into end offsets.  The second pass over the block's
+// 64 KiB (histogram first, then encode) is served by the L2.
+template <bool BUILD>
+__global__ void __launch_bounds__(kMaxBlockWarps * 32)
+block_encode_fused_kernel(const uint8_t* __restrict__ in, uint32_t n_blocks, uint32_t block_size, uint16_t* __restrict__ block_freqs,
+                          uint32_t chunk_syms, uint8_t* __restrict__ scratch, uint32_t slot_bytes, uint64_t* __restrict__ look,
+                          uint32_t* __restrict__ counter, uint8_t* __restrict__ blob, uint64_t blob_cap, uint64_t* __restrict__ offsets,
+                          uint32_t* __restrict__ status)
+{
+    extern __shared__ __align__(1024) uint8_t s_enc[];          // [32 KiB table][warps x 1 KiB stage + ring]
+    __shared__ __align__(16) BlockModelSmem sm;
+    __shared__ uint32_t s_flag[1];
+    __shared__ uint32_t s_block;
+    uint4* s_tab = reinterpret_cast<uint4*>(s_enc);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t per_block = block_size / chunk_syms;
+    const uint32_t n_chunks = n_blocks * per_block;
+    if (blockIdx.x == 0) {
+        if (warp == 0) fused_scanner(look, n_chunks, lane, status);
+        return;
+    }
+    const uint32_t warps = blockDim.x >> 5;
+    const uint32_t tab = smem_addr(s_enc), wsm = tab + kEncTableBytes + warp * kEncWarpSmem;
+    uint8_t* slots = scratch + (static_cast<uint64_t>(blockIdx.x - 1) * warps + warp) * 2 * slot_bytes;     // this warp's two slots
+    uint32_t pend_chunk = 0, pend_size = 0, parity = 0;
+    bool pending = false;
+    for (;;) {
+        __syncthreads();                                   // the previous block's table is no longer in use
+        if (tid == 0) s_block = atomicAdd(counter, 1u);
+        __syncthreads();
+        const uint32_t block = s_block;
+        if (block >= n_blocks) break;
+        const uint8_t* blk = in + static_cast<uint64_t>(block) * block_size;
+        uint16_t* freqs = block_freqs + static_cast<uint64_t>(block) * 256;
+        bool ok;
+        if (BUILD) {
+            block_model_build(blk, block_size, sm, freqs, status);
+            ok = block_prefix(&sm.h[0][0], sm.cum, &s_flag[0]);      // the widths are still in shared memory
+        } else {
+            ok = block_prefix(static_cast<const uint16_t*>(freqs), sm.cum, &s_flag[0]);
+        }
+        const bool r32 = block_build_enc_table(sm.cum, ok, s_tab);
+        if (warp < per_block) {
+            const uint32_t chunk = block * per_block + warp;
+            uint8_t* slot_end = slots + (parity + 1) * static_cast<uint64_t>(slot_bytes);
+            const uint8_t* src = blk + static_cast<uint64_t>(warp) * chunk_syms;
+            const uint32_t produced = r32 ? word_encode_stream<true>(src, chunk_syms, tab, wsm, slot_end, status)
+                                          : word_encode_stream<false>(src, chunk_syms, tab, wsm, slot_end, status);
+            if (lane == 0) st_relaxed_u64(look + chunk, kLookAgg | ((produced + 15u) & ~15u));
+            __syncwarp();
+            if (pending)
+                fused_place(look, pend_chunk, n_chunks, slots + (2 - parity) * static_cast<uint64_t>(slot_bytes), pend_size, blob, blob_cap,
+                            offsets, lane, status);
+            pend_chunk = chunk;
+            pend_size = produced;
+            pending = true;
+            parity ^= 1;
+            __syncwarp();
+        }
+    }
+    if (pending)
+        fused_place(look, pend_chunk, n_chunks, slots + (2 - parity) * static_cast<uint64_t>(slot_bytes), pend_size, blob, blob_cap, offsets,
+                    lane, status);
 }
 
 inline uint32_t block_threads(uint32_t block_size, uint32_t chunk_syms)
@@ -330,6 +423,37 @@ inline void configure_block_kernels()
     cudaFuncSetAttribute(block_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxBlockWarps * kRingBytes);
     cudaFuncSetAttribute(block_encode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(block_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncTableBytes + kMaxBlockWarps * kEncWarpSmem);
+    cudaFuncSetAttribute(block_encode_fused_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(block_encode_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncTableBytes + kMaxBlockWarps * kEncWarpSmem);
+    cudaFuncSetAttribute(block_encode_fused_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(block_encode_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncTableBytes + kMaxBlockWarps * kEncWarpSmem);
+}
+
+// grid of the fused per-block encoder: CTA 0 (scanner) + as many worker CTAs as are resident at once
+inline uint32_t block_fused_grid(uint32_t sms, uint32_t n_blocks, uint32_t threads, bool build)
+{
+    int per_sm = 0;
+    const size_t smem = kEncTableBytes + (threads / 32) * kEncWarpSmem;
+    if (build) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, block_encode_fused_kernel<true>, static_cast<int>(threads), smem);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, block_encode_fused_kernel<false>, static_cast<int>(threads), smem);
+    if (per_sm < 1) per_sm = 1;
+    uint64_t workers = static_cast<uint64_t>(sms) * per_sm - 1;       // the scanner CTA takes one slot
+    if (workers > n_blocks) workers = n_blocks;
+    if (workers < 1) workers = 1;
+    return static_cast<uint32_t>(workers + 1);
+}
+
+inline void launch_block_encode_fused(cudaStream_t stream, uint32_t grid, uint32_t threads, bool build, const uint8_t* d_in, uint32_t n_blocks,
+                                      uint32_t block_size, uint16_t* d_freqs, uint32_t chunk_syms, uint8_t* scratch, uint32_t slot,
+                                      uint64_t* look, uint32_t* counter, uint8_t* blob, uint64_t blob_cap, uint64_t* offsets, uint32_t* status)
+{
+    const size_t smem = kEncTableBytes + (threads / 32) * kEncWarpSmem;
+    if (build)
+        block_encode_fused_kernel<true><<<grid, threads, smem, stream>>>(d_in, n_blocks, block_size, d_freqs, chunk_syms, scratch, slot, look,
+                                                                          counter, blob, blob_cap, offsets, status);
+    else
+        block_encode_fused_kernel<false><<<grid, threads, smem, stream>>>(d_in, n_blocks, block_size, d_freqs, chunk_syms, scratch, slot, look,
+                                                                           counter, blob, blob_cap, offsets, status);
 }
 
 inline void launch_block_encode(cudaStream_t stream, const uint8_t* d_in, uint32_t n_blocks, uint32_t block_size,

@@ -122,4 +122,45 @@ __device__ __forceinline__ void stg_stream_u128(uint4* p, uint4 v)
                  : "memory");
 }
 
+
+// ---- L2 residency hints (createpolicy + .L2::cache_hint).  The fused encoders park every finished stream in a
+// per-warp scratch slot until its final position is known; marking those lines evict_last and the one-pass streams
+// (symbols in, blob out) evict_first keeps the scratch in the 126 MB L2 instead of making an HBM round trip.
+__device__ __forceinline__ uint64_t l2_policy_keep()
+{
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_stream()
+{
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void stg_hint_u128(uint4* p, uint4 v, uint64_t policy)
+{
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w), "l"(policy)
+                 : "memory");
+}
+// L2-coherent load (data this kernel wrote itself) with a residency hint
+__device__ __forceinline__ uint4 ldg_cg_hint_u128(const uint4* p, uint64_t policy)
+{
+    uint4 v;
+    asm volatile("ld.global.cg.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p), "l"(policy)
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 ldg_stream_hint_u128(const uint4* p, uint64_t policy)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p), "l"(policy));
+    return v;
+}
+
 }  // namespace rb200

@@ -642,6 +642,19 @@ int reserve_dir(rb200_ctx* ctx, size_t entries)
     return RB200_OK;
 }
 
+// An error exit of a host pipeline must not leave copies in flight: they target the caller's buffers and the context's
+// staging, which a later reserve() may free.  Also clears whatever the kernels flagged.
+int fail_pipeline(rb200_ctx* ctx, int rc)
+{
+    cudaStreamSynchronize(ctx->s_in);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->s_out);
+    cudaMemsetAsync(ctx->d_status, 0, sizeof(uint32_t), ctx->stream);
+    cudaMemsetAsync(ctx->d_work, 0, sizeof(DecodeWork), ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    return rc;
+}
+
 // One pipeline slice of a host-mode call: chunks [c0, c0 + cnt) = symbols [lo, lo + len).
 struct Slice {
     size_t c0, cnt, lo, len;
@@ -730,13 +743,13 @@ int encode_host(rb200_ctx* ctx, const rb200_model* model, const uint8_t* in, siz
     };
 
     rc = issue(0);
-    if (rc != RB200_OK) return rc;
+    if (rc != RB200_OK) return fail_pipeline(ctx, rc);
     size_t base = 0;
     bool overflow = false;
     for (size_t i = 0; i < n_slices; i++) {
         if (i + 1 < n_slices) {
             rc = issue(i + 1);
-            if (rc != RB200_OK) return rc;
+            if (rc != RB200_OK) return fail_pipeline(ctx, rc);
         }
         RB_CUDA(ctx, cudaEventSynchronize(ctx->ev_done[i]));          // slice i's size is now on the host
         const size_t total = static_cast<size_t>(ctx->h_slice_total[i]);
@@ -806,7 +819,7 @@ int decode_host(rb200_ctx* ctx, const rb200_model* model, const uint8_t* blob, s
         RB_CUDA(ctx, cudaEventRecord(ctx->ev_in[i], ctx->s_in));
         RB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[i], 0));
         rc = decode_device(ctx, model, d_blob, blob_size, d_off + s.c0, chunk_syms, d_out + s.lo, s.len);
-        if (rc != RB200_OK) return rc;
+        if (rc != RB200_OK) return fail_pipeline(ctx, rc);
         RB_CUDA(ctx, cudaEventRecord(ctx->ev_done[i], ctx->stream));
         RB_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_done[i], 0));
         RB_CUDA(ctx, cudaMemcpyAsync(out + s.lo, d_out + s.lo, s.len, cudaMemcpyDeviceToHost, ctx->s_out));
@@ -928,14 +941,30 @@ extern "C" int rb200_blocks_build_models(rb200_ctx* ctx, const uint8_t* in, uint
 
 namespace {
 
-int blocks_encode_device(rb200_ctx* ctx, const uint8_t* d_in, uint32_t n_blocks, uint32_t block_size, const uint16_t* d_freqs,
-                         uint32_t chunk_syms, uint8_t* d_blob, size_t blob_cap, uint64_t* d_offsets)
+// Per-block encode.  Default: ONE persistent launch (block_encode_fused_kernel: [model,] tables, encode, directory,
+// placement); build_models makes the kernel run count_freqs + normalize_freqs per block first and write d_freqs.
+// RB200_ENCODE_PATH=split keeps the round-1 sequence (encode into per-chunk slots, tile scan, compaction).
+int blocks_encode_device(rb200_ctx* ctx, const uint8_t* d_in, uint32_t n_blocks, uint32_t block_size, uint16_t* d_freqs,
+                         bool build_models, uint32_t chunk_syms, uint8_t* d_blob, size_t blob_cap, uint64_t* d_offsets)
 {
     const uint32_t per_block = block_size / chunk_syms;
     const uint64_t n_chunks64 = static_cast<uint64_t>(n_blocks) * per_block;
     if (n_chunks64 >= (1ull << 31)) return RB200_E_ARG;
     const uint32_t n_chunks = static_cast<uint32_t>(n_chunks64);
     const uint32_t slot = slot_bytes_for(chunk_syms);
+    if (use_fused_encode(chunk_syms) || build_models) {
+        const uint32_t threads = block_threads(block_size, chunk_syms);
+        const uint32_t grid = block_fused_grid(static_cast<uint32_t>(ctx->sms), n_blocks, threads, build_models);
+        int rc = reserve(ctx, ctx->scratch, static_cast<size_t>(grid) * (threads / 32) * 2 * slot + 16);   // two slots per resident warp
+        if (rc == RB200_OK) rc = reserve(ctx, ctx->sizes, 16 + static_cast<size_t>(n_chunks) * sizeof(uint64_t));
+        if (rc != RB200_OK) return rc;
+        uint32_t* counter = static_cast<uint32_t*>(ctx->sizes.p);
+        uint64_t* look = reinterpret_cast<uint64_t*>(static_cast<uint8_t*>(ctx->sizes.p) + 16);
+        RB_CUDA(ctx, cudaMemsetAsync(ctx->sizes.p, 0, 16 + static_cast<size_t>(n_chunks) * sizeof(uint64_t), ctx->stream));
+        launch_block_encode_fused(ctx->stream, grid, threads, build_models, d_in, n_blocks, block_size, d_freqs, chunk_syms,
+                                  static_cast<uint8_t*>(ctx->scratch.p), slot, look, counter, d_blob, blob_cap, d_offsets, ctx->d_status);
+        return check_launch(ctx, "block_encode_fused_kernel");
+    }
     uint8_t* scratch; uint32_t* sizes; uint64_t* tile_sums;
     int rc = reserve_encode_workspace(ctx, n_chunks, slot, &scratch, &sizes, &tile_sums);
     if (rc != RB200_OK) return rc;
@@ -945,9 +974,165 @@ int blocks_encode_device(rb200_ctx* ctx, const uint8_t* d_in, uint32_t n_blocks,
     return finish_encode(ctx, scratch, slot, sizes, tile_sums, n_chunks, d_blob, blob_cap, d_offsets);
 }
 
+// one CTA per block, one warp per chunk of the block: at most 32 chunks per block
 bool blocks_geometry_ok(uint32_t n_blocks, uint32_t block_size, uint32_t chunk_syms)
 {
     return n_blocks && block_size && chunk_ok(chunk_syms) && block_size % chunk_syms == 0 && block_size / chunk_syms <= 32;
+}
+
+
+// Host buffers -> blob for the per-block path, overlapped like encode_host: slices of whole blocks; slice i+1 is
+// copied in (with its frequency tables when the caller supplies them) while slice i is encoded and slice i-1 is copied
+// out (blob, directory, and the frequency tables when the kernel built them).
+int blocks_encode_host(rb200_ctx* ctx, const uint8_t* in, uint32_t n_blocks, uint32_t block_size, uint16_t* block_freqs, bool build,
+                       uint32_t chunk_syms, uint8_t* blob, size_t blob_cap, uint64_t* offsets, size_t* blob_size)
+{
+    const uint32_t per_block = block_size / chunk_syms;
+    const size_t n = static_cast<size_t>(n_blocks) * block_size;
+    const size_t n_chunks = static_cast<size_t>(n_blocks) * per_block;
+    Slice sl[rb200_ctx::kMaxSlices];                         // planned in units of blocks: c0 / cnt count blocks here
+    const size_t n_slices = plan_slices(n, block_size, sl);
+    const size_t slot = slot_bytes_for(chunk_syms);
+    const size_t fbytes = static_cast<size_t>(n_blocks) * 256 * sizeof(uint16_t);
+    int rc = reserve(ctx, ctx->st_in, n + 16);
+    if (rc == RB200_OK) rc = reserve(ctx, ctx->st_blob, n_chunks * slot + 16);
+    if (rc == RB200_OK) rc = reserve(ctx, ctx->st_offsets, (n_chunks + n_slices) * sizeof(uint64_t));
+    if (rc == RB200_OK) rc = reserve(ctx, ctx->st_aux, fbytes);
+    if (rc == RB200_OK) rc = reserve_dir(ctx, n_chunks + n_slices);
+    if (rc != RB200_OK) return rc;
+    uint8_t* d_in = static_cast<uint8_t*>(ctx->st_in.p);
+    uint8_t* d_blob = static_cast<uint8_t*>(ctx->st_blob.p);
+    uint64_t* d_off = static_cast<uint64_t*>(ctx->st_offsets.p);
+    uint16_t* d_freqs = static_cast<uint16_t*>(ctx->st_aux.p);
+
+    RB_CUDA(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
+    RB_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_start, 0));
+    RB_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_start, 0));
+
+    auto issue = [&](size_t i) -> int {
+        const Slice& s = sl[i];
+        const size_t c0 = s.c0 * per_block, cnt = s.cnt * per_block;          // chunks of this slice
+        RB_CUDA(ctx, cudaMemcpyAsync(d_in + s.lo, in + s.lo, s.len, cudaMemcpyHostToDevice, ctx->s_in));
+        if (!build)
+            RB_CUDA(ctx, cudaMemcpyAsync(d_freqs + s.c0 * 256, block_freqs + s.c0 * 256, s.cnt * 256 * sizeof(uint16_t),
+                                         cudaMemcpyHostToDevice, ctx->s_in));
+        RB_CUDA(ctx, cudaEventRecord(ctx->ev_in[i], ctx->s_in));
+        RB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[i], 0));
+        uint64_t* so = d_off + c0 + i;
+        int r = blocks_encode_device(ctx, d_in + s.lo, static_cast<uint32_t>(s.cnt), block_size, d_freqs + s.c0 * 256, build, chunk_syms,
+                                     d_blob + c0 * slot, cnt * slot, so);
+        if (r != RB200_OK) return r;
+        RB_CUDA(ctx, cudaMemcpyAsync(&ctx->h_slice_total[i], so + cnt, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        RB_CUDA(ctx, cudaEventRecord(ctx->ev_done[i], ctx->stream));
+        return RB200_OK;
+    };
+    rc = issue(0);
+    if (rc != RB200_OK) return fail_pipeline(ctx, rc);
+    size_t base = 0;
+    bool overflow = false;
+    for (size_t i = 0; i < n_slices; i++) {
+        if (i + 1 < n_slices) {
+            rc = issue(i + 1);
+            if (rc != RB200_OK) return fail_pipeline(ctx, rc);
+        }
+        RB_CUDA(ctx, cudaEventSynchronize(ctx->ev_done[i]));
+        const size_t total = static_cast<size_t>(ctx->h_slice_total[i]);
+        const Slice& s = sl[i];
+        const size_t c0 = s.c0 * per_block, cnt = s.cnt * per_block;
+        if (base + total > blob_cap) {
+            overflow = true;
+        } else if (!overflow) {
+            RB_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_done[i], 0));
+            RB_CUDA(ctx, cudaMemcpyAsync(blob + base, d_blob + c0 * slot, total, cudaMemcpyDeviceToHost, ctx->s_out));
+            RB_CUDA(ctx, cudaMemcpyAsync(ctx->h_dir + c0 + i, d_off + c0 + i, cnt * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->s_out));
+            if (build)
+                RB_CUDA(ctx, cudaMemcpyAsync(block_freqs + s.c0 * 256, d_freqs + s.c0 * 256, s.cnt * 256 * sizeof(uint16_t),
+                                             cudaMemcpyDeviceToHost, ctx->s_out));
+        }
+        ctx->h_slice_total[i] = base;
+        base += total;
+    }
+    RB_CUDA(ctx, cudaEventRecord(ctx->ev_out, ctx->s_out));
+    RB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_out, 0));
+    rc = rb200_sync(ctx);
+    if (rc != RB200_OK) return rc;
+    if (overflow) return RB200_E_SPACE;
+    for (size_t i = 0; i < n_slices; i++) {                  // rebase the directory into the caller's array
+        const uint64_t add = ctx->h_slice_total[i];
+        const size_t c0 = sl[i].c0 * per_block, cnt = sl[i].cnt * per_block;
+        const uint64_t* src = ctx->h_dir + c0 + i;
+        uint64_t* dst = offsets + c0;
+        for (size_t c = 0; c < cnt; c++) dst[c] = src[c] + add;
+    }
+    offsets[n_chunks] = base;
+    if (blob_size) *blob_size = base;
+    return RB200_OK;
+}
+
+int blocks_decode_host(rb200_ctx* ctx, const uint8_t* blob, size_t blob_size, const uint64_t* offsets, const uint16_t* block_freqs,
+                       uint32_t n_blocks, uint32_t block_size, uint32_t chunk_syms, uint8_t* out)
+{
+    const uint32_t per_block = block_size / chunk_syms;
+    const size_t n = static_cast<size_t>(n_blocks) * block_size;
+    const size_t n_chunks = static_cast<size_t>(n_blocks) * per_block;
+    if (offsets[n_chunks] != blob_size) return RB200_E_STREAM;
+    Slice sl[rb200_ctx::kMaxSlices];                         // units of blocks
+    const size_t n_slices = plan_slices(n, block_size, sl);
+    const size_t fbytes = static_cast<size_t>(n_blocks) * 256 * sizeof(uint16_t);
+    int rc = reserve(ctx, ctx->st_blob, blob_size + 16);
+    if (rc == RB200_OK) rc = reserve(ctx, ctx->st_offsets, (n_chunks + 1) * sizeof(uint64_t));
+    if (rc == RB200_OK) rc = reserve(ctx, ctx->st_out, n + 16);
+    if (rc == RB200_OK) rc = reserve(ctx, ctx->st_aux, fbytes);
+    if (rc == RB200_OK) rc = reserve_dir(ctx, n_chunks + 1);
+    if (rc != RB200_OK) return rc;
+    uint8_t* d_blob = static_cast<uint8_t*>(ctx->st_blob.p);
+    uint64_t* d_off = static_cast<uint64_t*>(ctx->st_offsets.p);
+    uint8_t* d_out = static_cast<uint8_t*>(ctx->st_out.p);
+    uint16_t* d_freqs = static_cast<uint16_t*>(ctx->st_aux.p);
+    for (size_t c = 0; c < n_chunks; c++) {                  // the copies below trust these
+        if (offsets[c] > offsets[c + 1] || offsets[c + 1] > blob_size) return RB200_E_STREAM;
+        ctx->h_dir[c] = offsets[c];
+    }
+    ctx->h_dir[n_chunks] = offsets[n_chunks];
+
+    RB_CUDA(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
+    RB_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_start, 0));
+    RB_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_start, 0));
+    RB_CUDA(ctx, cudaMemcpyAsync(d_off, ctx->h_dir, (n_chunks + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->s_in));
+    for (size_t i = 0; i < n_slices; i++) {
+        const Slice& s = sl[i];
+        const size_t c0 = s.c0 * per_block, c1 = (s.c0 + s.cnt) * per_block;
+        const size_t b0 = c0 ? static_cast<size_t>(offsets[c0] & ~15ull) : 0;
+        const size_t b1 = static_cast<size_t>(offsets[c1] & ~15ull);
+        if (b1 > b0) RB_CUDA(ctx, cudaMemcpyAsync(d_blob + b0, blob + b0, b1 - b0, cudaMemcpyHostToDevice, ctx->s_in));
+        RB_CUDA(ctx, cudaMemcpyAsync(d_freqs + s.c0 * 256, block_freqs + s.c0 * 256, s.cnt * 256 * sizeof(uint16_t), cudaMemcpyHostToDevice,
+                                     ctx->s_in));
+        RB_CUDA(ctx, cudaEventRecord(ctx->ev_in[i], ctx->s_in));
+        RB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[i], 0));
+        launch_block_decode(ctx->stream, d_blob, blob_size, d_off + c0, d_freqs + s.c0 * 256, static_cast<uint32_t>(s.cnt), block_size,
+                            chunk_syms, d_out + s.lo, ctx->d_status);
+        rc = check_launch(ctx, "block_decode_kernel");
+        if (rc != RB200_OK) return fail_pipeline(ctx, rc);
+        RB_CUDA(ctx, cudaEventRecord(ctx->ev_done[i], ctx->stream));
+        RB_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_done[i], 0));
+        RB_CUDA(ctx, cudaMemcpyAsync(out + s.lo, d_out + s.lo, s.len, cudaMemcpyDeviceToHost, ctx->s_out));
+    }
+    RB_CUDA(ctx, cudaEventRecord(ctx->ev_out, ctx->s_out));
+    RB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_out, 0));
+    return rb200_sync(ctx);
+}
+
+int blocks_encode_entry(rb200_ctx* ctx, const uint8_t* in, uint32_t n_blocks, uint32_t block_size, uint16_t* block_freqs, bool build,
+                        uint32_t chunk_syms, uint8_t* blob, size_t blob_cap, uint64_t* offsets, size_t* blob_size, int mem_kind)
+{
+    if (!ctx || !in || !block_freqs || !blob || !offsets || !blocks_geometry_ok(n_blocks, block_size, chunk_syms)) return RB200_E_ARG;
+    DeviceGuard g(ctx->device);
+    if (mem_kind == RB200_MEM_DEVICE) {
+        if (!aligned16(blob) || (reinterpret_cast<uintptr_t>(offsets) & 7)) return RB200_E_ARG;
+        return blocks_encode_device(ctx, in, n_blocks, block_size, block_freqs, build, chunk_syms, blob, blob_cap, offsets);
+    }
+    if (mem_kind != RB200_MEM_HOST) return RB200_E_ARG;
+    return blocks_encode_host(ctx, in, n_blocks, block_size, block_freqs, build, chunk_syms, blob, blob_cap, offsets, blob_size);
 }
 
 }  // namespace
@@ -956,38 +1141,15 @@ extern "C" int rb200_blocks_encode(rb200_ctx* ctx, const uint8_t* in, uint32_t n
                                    const uint16_t* block_freqs, uint32_t chunk_syms, uint8_t* blob, size_t blob_cap,
                                    uint64_t* offsets, size_t* blob_size, int mem_kind)
 {
-    if (!ctx || !in || !block_freqs || !blob || !offsets || !blocks_geometry_ok(n_blocks, block_size, chunk_syms)) return RB200_E_ARG;
-    DeviceGuard g(ctx->device);
-    const size_t n = static_cast<size_t>(n_blocks) * block_size;
-    const size_t n_chunks = static_cast<size_t>(n_blocks) * (block_size / chunk_syms);
-    if (mem_kind == RB200_MEM_DEVICE) {
-        if (!aligned16(blob) || (reinterpret_cast<uintptr_t>(offsets) & 7)) return RB200_E_ARG;
-        return blocks_encode_device(ctx, in, n_blocks, block_size, block_freqs, chunk_syms, blob, blob_cap, offsets);
-    }
-    if (mem_kind != RB200_MEM_HOST) return RB200_E_ARG;
-    const size_t bound = rb200_encode_bound(n, chunk_syms);
-    const size_t fbytes = static_cast<size_t>(n_blocks) * 256 * sizeof(uint16_t);
-    int rc = reserve(ctx, ctx->st_in, n + 16);
-    if (rc == RB200_OK) rc = reserve(ctx, ctx->st_blob, bound + 16);
-    if (rc == RB200_OK) rc = reserve(ctx, ctx->st_offsets, (n_chunks + 1) * sizeof(uint64_t));
-    if (rc == RB200_OK) rc = reserve(ctx, ctx->st_aux, fbytes);
-    if (rc != RB200_OK) return rc;
-    RB_CUDA(ctx, cudaMemcpyAsync(ctx->st_in.p, in, n, cudaMemcpyHostToDevice, ctx->stream));
-    RB_CUDA(ctx, cudaMemcpyAsync(ctx->st_aux.p, block_freqs, fbytes, cudaMemcpyHostToDevice, ctx->stream));
-    uint64_t* d_off = static_cast<uint64_t*>(ctx->st_offsets.p);
-    rc = blocks_encode_device(ctx, static_cast<const uint8_t*>(ctx->st_in.p), n_blocks, block_size,
-                              static_cast<const uint16_t*>(ctx->st_aux.p), chunk_syms, static_cast<uint8_t*>(ctx->st_blob.p),
-                              bound, d_off);
-    if (rc != RB200_OK) return rc;
-    RB_CUDA(ctx, cudaMemcpyAsync(offsets, d_off, (n_chunks + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    rc = rb200_sync(ctx);
-    if (rc != RB200_OK) return rc;
-    const size_t total = static_cast<size_t>(offsets[n_chunks]);
-    if (total > blob_cap) return RB200_E_SPACE;
-    RB_CUDA(ctx, cudaMemcpyAsync(blob, ctx->st_blob.p, total, cudaMemcpyDeviceToHost, ctx->stream));
-    RB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (blob_size) *blob_size = total;
-    return RB200_OK;
+    return blocks_encode_entry(ctx, in, n_blocks, block_size, const_cast<uint16_t*>(block_freqs), false, chunk_syms, blob, blob_cap, offsets,
+                               blob_size, mem_kind);
+}
+
+extern "C" int rb200_blocks_model_encode(rb200_ctx* ctx, const uint8_t* in, uint32_t n_blocks, uint32_t block_size,
+                                         uint16_t* block_freqs, uint32_t chunk_syms, uint8_t* blob, size_t blob_cap,
+                                         uint64_t* offsets, size_t* blob_size, int mem_kind)
+{
+    return blocks_encode_entry(ctx, in, n_blocks, block_size, block_freqs, true, chunk_syms, blob, blob_cap, offsets, blob_size, mem_kind);
 }
 
 extern "C" int rb200_blocks_decode(rb200_ctx* ctx, const uint8_t* blob, size_t blob_size, const uint64_t* offsets,
@@ -996,8 +1158,8 @@ extern "C" int rb200_blocks_decode(rb200_ctx* ctx, const uint8_t* blob, size_t b
 {
     if (!ctx || !blob || !offsets || !block_freqs || !out || !blocks_geometry_ok(n_blocks, block_size, chunk_syms)) return RB200_E_ARG;
     if (blob_size & 15) return RB200_E_ARG;
+    if (blob_size >> 36) return RB200_E_ARG;
     DeviceGuard g(ctx->device);
-    const size_t n = static_cast<size_t>(n_blocks) * block_size;
     const size_t n_chunks = static_cast<size_t>(n_blocks) * (block_size / chunk_syms);
     if (n_chunks >= (1ull << 31)) return RB200_E_ARG;
     if (mem_kind == RB200_MEM_DEVICE) {
@@ -1006,22 +1168,7 @@ extern "C" int rb200_blocks_decode(rb200_ctx* ctx, const uint8_t* blob, size_t b
         return check_launch(ctx, "block_decode_kernel");
     }
     if (mem_kind != RB200_MEM_HOST) return RB200_E_ARG;
-    const size_t fbytes = static_cast<size_t>(n_blocks) * 256 * sizeof(uint16_t);
-    int rc = reserve(ctx, ctx->st_blob, blob_size + 16);
-    if (rc == RB200_OK) rc = reserve(ctx, ctx->st_offsets, (n_chunks + 1) * sizeof(uint64_t));
-    if (rc == RB200_OK) rc = reserve(ctx, ctx->st_out, n + 16);
-    if (rc == RB200_OK) rc = reserve(ctx, ctx->st_aux, fbytes);
-    if (rc != RB200_OK) return rc;
-    RB_CUDA(ctx, cudaMemcpyAsync(ctx->st_blob.p, blob, blob_size, cudaMemcpyHostToDevice, ctx->stream));
-    RB_CUDA(ctx, cudaMemcpyAsync(ctx->st_offsets.p, offsets, (n_chunks + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
-    RB_CUDA(ctx, cudaMemcpyAsync(ctx->st_aux.p, block_freqs, fbytes, cudaMemcpyHostToDevice, ctx->stream));
-    launch_block_decode(ctx->stream, static_cast<const uint8_t*>(ctx->st_blob.p), blob_size,
-                        static_cast<const uint64_t*>(ctx->st_offsets.p), static_cast<const uint16_t*>(ctx->st_aux.p), n_blocks,
-                        block_size, chunk_syms, static_cast<uint8_t*>(ctx->st_out.p), ctx->d_status);
-    rc = check_launch(ctx, "block_decode_kernel");
-    if (rc != RB200_OK) return rc;
-    RB_CUDA(ctx, cudaMemcpyAsync(out, ctx->st_out.p, n, cudaMemcpyDeviceToHost, ctx->stream));
-    return rb200_sync(ctx);
+    return blocks_decode_host(ctx, blob, blob_size, offsets, block_freqs, n_blocks, block_size, chunk_syms, out);
 }
 
 // ---------------------------------------------------------------------------

@@ -310,7 +310,9 @@ __device__ __forceinline__ void word_enc_step(WordEncState& st, uint32_t sym, ui
     }
 }
 
-// flush every complete 16-byte vector of the ring; *flushed = bytes already written below slot_end
+// flush every complete 16-byte vector of the ring; *flushed = bytes already written below slot_end.
+// KEEP: the destination is a scratch slot that is read back soon (fused paths): ask the L2 to hold on to it.
+template <bool KEEP = false>
 __device__ __forceinline__ void word_enc_flush(uint32_t produced, uint32_t& flushed, uint32_t ring, uint8_t* slot_end, uint32_t lane)
 {
     const uint32_t nvec = (produced - flushed) >> 4;
@@ -318,7 +320,8 @@ __device__ __forceinline__ void word_enc_flush(uint32_t produced, uint32_t& flus
     if (lane < nvec) {
         const uint32_t v = (flushed >> 4) + lane + 1;                 // vector v ends 16 * (v - 1) bytes below slot_end
         const uint4 q = lds_u128(ring + ((0u - 16u * v) & (kEncRingBytes - 1)));
-        stg_stream_u128(reinterpret_cast<uint4*>(slot_end - 16ull * v), q);
+        if (KEEP) stg_hint_u128(reinterpret_cast<uint4*>(slot_end - 16ull * v), q, l2_policy_keep());
+        else stg_stream_u128(reinterpret_cast<uint4*>(slot_end - 16ull * v), q);
     }
     flushed += nvec << 4;
     __syncwarp();
@@ -328,7 +331,8 @@ __device__ __forceinline__ void word_enc_flush(uint32_t produced, uint32_t& flus
 // downwards; returns the stream size in bytes (warp-uniform).
 //   tab  = shared address of the 8x replicated uint4 table
 //   wsm  = shared address of this warp's 1 KiB (stage, then ring; 512-byte aligned)
-template <bool R32>
+//   KEEP = the slot is scratch that is read back soon (see word_enc_flush)
+template <bool R32, bool KEEP = false>
 __device__ __forceinline__ uint32_t word_encode_stream(const uint8_t* __restrict__ chunk_in, uint32_t m, uint32_t tab, uint32_t wsm,
                                                        uint8_t* __restrict__ slot_end, uint32_t* __restrict__ status)
 {
@@ -357,9 +361,9 @@ __device__ __forceinline__ uint32_t word_encode_stream(const uint8_t* __restrict
     for (uint32_t g = steps; g > nblk * 16; g--) {
         const uint32_t s = chunk_in[static_cast<uint64_t>(g - 1) * 32 + lane];
         word_enc_step<R32, true>(st, s, tab_lane, ring, gt, true);
-        if (((g - 1) & 3) == 0) word_enc_flush(kEncRingBytes - 2 - st.wpos, flushed, ring, slot_end, lane);
+        if (((g - 1) & 3) == 0) word_enc_flush<KEEP>(kEncRingBytes - 2 - st.wpos, flushed, ring, slot_end, lane);
     }
-    word_enc_flush(kEncRingBytes - 2 - st.wpos, flushed, ring, slot_end, lane);
+    word_enc_flush<KEEP>(kEncRingBytes - 2 - st.wpos, flushed, ring, slot_end, lane);
 
     for (uint32_t b = nblk; b-- > 0;) {
         __syncwarp();
@@ -377,19 +381,25 @@ __device__ __forceinline__ uint32_t word_encode_stream(const uint8_t* __restrict
 #pragma unroll
             for (int j = 3; j >= 0; j--)
                 word_enc_step<R32, true>(st, lds_u8(stage + (grp * 4 + j) * 32 + lane), tab_lane, ring, gt, true);
-            // <= 256 bytes per 4 steps; flushing whenever >= 256 are pending keeps the 512-byte ring safe
-            if (kEncRingBytes - 2 - st.wpos - flushed >= 256) word_enc_flush(kEncRingBytes - 2 - st.wpos, flushed, ring, slot_end, lane);
+            // <= 256 bytes per 4 steps; flushing whenever >= 256 are pending keeps the 512-byte ring safe.  The test is
+            // warp-uniform; voting on it tells ptxas so (a uniform branch: no convergence check before the next ballot)
+#if RB200_ENC_UNIFORM_FLUSH
+            if (__any_sync(0xffffffffu, kEncRingBytes - 2 - st.wpos - flushed >= 256))
+#else
+            if (kEncRingBytes - 2 - st.wpos - flushed >= 256)
+#endif
+                word_enc_flush<KEEP>(kEncRingBytes - 2 - st.wpos, flushed, ring, slot_end, lane);
         }
     }
 
     // RansWordEncFlush for lanes 31..0 (main_simd.cpp:298-299): lane 31's hi word first (highest), lane 0's lo word last
-    word_enc_flush(kEncRingBytes - 2 - st.wpos, flushed, ring, slot_end, lane);     // < 16 bytes stay pending
+    word_enc_flush<KEEP>(kEncRingBytes - 2 - st.wpos, flushed, ring, slot_end, lane);     // < 16 bytes stay pending
     const uint32_t hpos = st.wpos - 4u * (31 - lane);
     sts_u16(ring | (hpos & (kEncRingBytes - 1)), st.x >> 16);
     sts_u16(ring | ((hpos - 2) & (kEncRingBytes - 1)), st.x);
     st.wpos -= kHeaderBytes;
     const uint32_t produced = kEncRingBytes - 2 - st.wpos;           // total stream bytes
-    word_enc_flush(produced, flushed, ring, slot_end, lane);
+    word_enc_flush<KEEP>(produced, flushed, ring, slot_end, lane);
     const uint32_t left = produced - flushed;                        // < 16, even: head of the stream, not vector aligned
     if (2 * lane < left) {
         const uint32_t off = flushed + 2 * lane + 2;                 // bytes below slot_end
@@ -411,6 +421,12 @@ __device__ __forceinline__ void word_encode_chunk(const uint8_t* __restrict__ ch
 
 #ifndef RB200_ENC_MINBLOCKS
 #define RB200_ENC_MINBLOCKS 3
+#endif
+#ifndef RB200_ENC_UNIFORM_FLUSH
+#define RB200_ENC_UNIFORM_FLUSH 1      // vote on the (warp-uniform) flush test so that ptxas emits a uniform branch
+#endif
+#ifndef RB200_ENC_KEEP_HINT
+#define RB200_ENC_KEEP_HINT false      // evict_last hint on the fused encoder's scratch stores (see word_enc_flush)
 #endif
 template <bool R32>
 __global__ void __launch_bounds__(kEncWarps * 32, RB200_ENC_MINBLOCKS)
@@ -480,7 +496,7 @@ __device__ __forceinline__ void place_stream(const uint8_t* src_end, uint32_t si
     uint4* d4 = reinterpret_cast<uint4*>(dst_vec0 + 16);
     const uint32_t nvec = padded / 16 - 1;
     uint32_t v = lane;
-    for (; v + 96 < nvec; v += 128) {                      // four loads in flight per lane: the scratch is mostly in HBM by now
+    for (; v + 96 < nvec; v += 128) {                      // four loads in flight per lane
         const uint4 a = ldg_l2_u128(s4 + v), b = ldg_l2_u128(s4 + v + 32), c = ldg_l2_u128(s4 + v + 64), d = ldg_l2_u128(s4 + v + 96);
         stg_stream_u128(d4 + v, a);
         stg_stream_u128(d4 + v + 32, b);
@@ -606,9 +622,13 @@ word_encode_fused_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t ch
         const uint64_t first = static_cast<uint64_t>(chunk) * chunk_syms;
         const uint32_t m = static_cast<uint32_t>(min(static_cast<uint64_t>(chunk_syms), n - first));
         uint8_t* slot_end = slots + (parity + 1) * static_cast<uint64_t>(slot_bytes);
-        const uint32_t produced = word_encode_stream<R32>(in + first, m, tab, wsm, slot_end, status);
+        const uint32_t produced = word_encode_stream<R32, RB200_ENC_KEEP_HINT>(in + first, m, tab, wsm, slot_end, status);
         if (lane == 0) st_relaxed_u64(look + chunk, kLookAgg | ((produced + 15u) & ~15u));
         __syncwarp();
+        // The previous chunk is placed only now, a whole chunk later.  Warps do not progress evenly (the issue arbiter
+        // favours high warp ids), so the scan front -- the oldest unfinished chunk -- trails the fastest warps by about one
+        // chunk time: placing 32 steps into the next chunk instead was measured at 2.39 ms per GiB against 1.15 ms,
+        // 580 M polling instructions (profiles/r2_encode_experiments.md).
         if (pending)
             fused_place(look, pend_chunk, n_chunks, slots + (2 - parity) * static_cast<uint64_t>(slot_bytes), pend_size, blob, blob_cap,
                         offsets, lane, status);

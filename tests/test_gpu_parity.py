@@ -269,6 +269,45 @@ def test_block_models_and_roundtrip(gpu_ctx, oracle_lib, gen, n_blocks, block_si
     _check_blocks(gpu_ctx, oracle_lib, _block_data(gen, n_blocks, block_size), n_blocks, block_size, chunk)
 
 
+@pytest.mark.parametrize("path", ["fused", "split"])
+def test_block_paths_and_host_pipeline(cuda_box, path):
+    """Per-block encode: the one-launch persistent path (default) and the round-1 sequence (RB200_ENCODE_PATH=split)
+    build the identical container; with 1 MiB slices the HOST-mode calls run their 3-stream pipeline over many slices of
+    whole blocks (encode, model+encode and decode) and must still match the oracle block by block."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r)
+import oracle, ryg_rans_b200 as rb
+rng = np.random.default_rng(21)
+orc = oracle.Oracle()
+ctx = rb.Context(0)
+for n_blocks, block_size, chunk in ((200, 65536, 8192), (37, 16384, 4096), (64, 65536, 65536)):
+    blocks = []
+    for b in range(n_blocks):
+        p = 1.0 / np.arange(1, 257) ** (0.6 + 0.1 * (b %% 9))
+        blocks.append(rng.permutation(256).astype(np.uint8)[rng.choice(256, block_size, p=p / p.sum())])
+    data = np.concatenate(blocks)
+    blob, offs, freqs = ctx.blocks_model_encode_host(data, n_blocks, block_size, chunk)
+    blob2, offs2 = ctx.blocks_encode_host(data, n_blocks, block_size, freqs, chunk)
+    assert np.array_equal(offs, offs2) and np.array_equal(blob, blob2)
+    per = block_size // chunk
+    for b in range(0, n_blocks, max(1, n_blocks // 7)):
+        f, c = orc.model(blocks[b], 12)
+        assert np.array_equal(f.astype(np.uint16), freqs[b])
+        ob, oo = orc.chunked_encode(oracle.CODER_WORD, blocks[b], f, c, chunk, scale_bits=12)
+        lo, hi = int(offs[b * per]) & ~15, int(offs[(b + 1) * per]) & ~15
+        assert np.array_equal(blob[lo:hi], ob), b
+    assert np.array_equal(ctx.blocks_decode_host(blob, offs, freqs, n_blocks, block_size, chunk), data)
+print("block paths ok", ctx.launches)
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RB200_ENCODE_PATH=path, RB200_SLICE_MIB="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "block paths ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
 def test_block_reciprocal_fallback(gpu_ctx, oracle_lib, gen):
     """Per-block encoders pick the 32-bit reciprocal when it is exact for the block's model; blocks whose model has
     a symbol of frequency 2964 or 3005 (the first that are not) must fall back, next to blocks that do not."""
@@ -286,10 +325,14 @@ def test_block_reciprocal_fallback(gpu_ctx, oracle_lib, gen):
 
 def _check_blocks(gpu_ctx, oracle_lib, data, n_blocks, block_size, chunk):
     freqs16 = gpu_ctx.blocks_build_models(data, n_blocks, block_size)
+    # the one-launch form (model + encode fused, rb200_blocks_model_encode) must give the same models and container
+    fblob, foffs, ffreqs = gpu_ctx.blocks_model_encode_host(data, n_blocks, block_size, chunk)
+    assert np.array_equal(ffreqs, freqs16)
     want = np.stack([oracle_lib.model(data[b * block_size:(b + 1) * block_size], 12)[0] for b in range(n_blocks)])
     assert np.array_equal(freqs16.astype(np.uint32), want), "device normalize_freqs differs from the reference algorithm"
 
     blob, offs = gpu_ctx.blocks_encode_host(data, n_blocks, block_size, freqs16, chunk)
+    assert np.array_equal(foffs, offs) and np.array_equal(fblob, blob), "fused model+encode container differs"
     # oracle: every block is its own container; containers concatenate because each ends 16-aligned
     parts, all_offs, base = [], [], 0
     for b in range(n_blocks):
