@@ -14,6 +14,7 @@
 #include "device_utils.cuh"
 #include "tables.h"
 #include "word_kernels.cuh"   // StreamWindow
+#include "word_decode_tma.cuh"   // persistent decode plumbing: DecPolicy, TmaWindow, tma_issue / tma_advance
 
 namespace rb200 {
 
@@ -42,10 +43,10 @@ __device__ __forceinline__ void alias_dec_step(uint32_t& x, uint32_t& cursor, ui
             const uint32_t bucket = xm >> (sb - 8);                        // :259
             const uint4 e = lds_u128_ro(mad_u32(bucket, kAliasDecReplicas * 16, tab_lane));
             const bool own = xm < e.x;                                     // :261 (bucket2 = 2 * bucket + 1)
-            const uint32_t fs = own ? e.z : e.y;                           // slot_freqs | sym_id << 17
+            const uint32_t fs = own ? e.z : e.y;                           // slot_freqs << 8 | sym_id
             const uint32_t adj = own ? (e.w >> 16) : (e.w & 0xffffu);
-            x = (fs & 0x1ffffu) * (x >> sb) + ((xm - adj) & 0xffffu);      // :265
-            *o = static_cast<uint8_t>(fs >> 17);                           // :266
+            x = (fs >> 8) * (x >> sb) + ((xm - adj) & 0xffffu);            // :265
+            *o = static_cast<uint8_t>(fs);                                 // :266
         } else {
             const uint32_t s = lds_u8_ro(tab_lane + xm);                   // cum2sym, main.cpp:200
             const uint32_t ds = lds_u32_ro(tab_lane + (1u << sb) + 4u * s);   // RansDecSymbol {start, freq}
@@ -187,6 +188,171 @@ alias_decode_kernel(const uint8_t* __restrict__ blob, uint64_t blob_size, const 
     if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(status, kStatStream);
 }
 constexpr uint32_t kAliasDecSmem = kAliasDecWarps * kRingBytes + 256 * kAliasDecReplicas * 16;   // 48 KiB
+
+// ---------------------------------------------------------------------------
+// K3p: the alias decoder on the persistent plumbing of word_decode_tma.cuh -- 2 CTAs of 24 warps per SM stay resident
+// and pull chunk ids from the context's atomic counter; the 32 KiB replicated bucket table is built once per CTA; the
+// per-warp stream window is the cp.async ring with a mirror behind it, wrapped once per 8 steps, so the two ranked byte
+// reads of RansDecRenorm need no address masking (round 1's kernel spends 5 of its ~20 ALU-pipe instructions per step
+// on that, and the ALU pipe is what binds it: 85 % busy, profiles/r2_ncu_summary.md).
+// ---------------------------------------------------------------------------
+using AliasDecShip = DecPolicy<20, 2, 8, kRefillCpAsync, 9, 0, 0, 0, false, 256 * kAliasDecReplicas * 16>;
+
+template <uint32_t SB>
+__device__ __forceinline__ void alias_dec_step_p(uint32_t& x, uint32_t& cur, uint32_t tab_lane, uint8_t* o, uint32_t lt, uint32_t sb_rt,
+                                                 bool active)
+{
+    const uint32_t sb = SB ? SB : sb_rt;
+    if (active) {
+        const uint32_t xm = x & ((1u << sb) - 1);                              // main_alias.cpp:258
+        const uint32_t bucket = xm >> (sb - 8);                                // :259
+        const uint4 e = lds_u128_ro(mad_u32(bucket, kAliasDecReplicas * 16, tab_lane));
+        const bool own = xm < e.x;                                             // :261 (bucket2 = 2 * bucket + 1)
+        const uint32_t fs = own ? e.z : e.y;                                   // slot_freqs << 8 | sym_id
+        const uint32_t adj = __byte_perm(e.w, 0u, own ? 0x4432u : 0x4410u);    // the taken half of the packed adjusts
+        x = mad_u32(fs >> 8, x >> sb, (xm - adj) & 0xffffu);                   // :265
+        *o = static_cast<uint8_t>(fs);                                         // :266
+    }
+    // RansDecRenorm (rans_byte.h:307-318) for the warp: 0, 1 or 2 bytes per lane, lane k's bytes before lane k+1's,
+    // most significant first.  Two predicates feed the votes, the ranked byte loads and the merges.
+    const uint32_t xr = active ? x : kByteL;
+    uint32_t xo = x;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p1, p2;\n\t"
+        ".reg .b32 m, r, a, b0, b1;\n\t"
+        "setp.lt.u32 p1, %2, %4;\n\t"
+        "setp.lt.u32 p2, %2, %5;\n\t"
+        "vote.sync.ballot.b32 m, p1, 0xffffffff;\n\t"
+        "and.b32 r, m, %3;\n\t"
+        "popc.b32 r, r;\n\t"
+        "add.u32 a, %1, r;\n\t"
+        "popc.b32 m, m;\n\t"
+        "add.u32 %1, %1, m;\n\t"
+        "vote.sync.ballot.b32 m, p2, 0xffffffff;\n\t"
+        "and.b32 r, m, %3;\n\t"
+        "popc.b32 r, r;\n\t"
+        "add.u32 a, a, r;\n\t"
+        "popc.b32 m, m;\n\t"
+        "add.u32 %1, %1, m;\n\t"
+        "ld.shared.u8 b0, [a];\n\t"              // unpredicated: ring + mirror make both reads safe for every lane
+        "ld.shared.u8 b1, [a+1];\n\t"
+        "@p1 mad.lo.u32 %0, %0, 256, b0;\n\t"
+        "@p2 mad.lo.u32 %0, %0, 256, b1;\n\t"
+        "}"
+        : "+r"(xo), "+r"(cur)
+        : "r"(xr), "r"(lt), "n"(kByteL), "n"(kByteL >> 8));
+    x = xo;
+}
+
+// kGroup steps: wrap (the mirror absorbed the previous group's overrun), fill check, steps
+template <uint32_t SB>
+__device__ __forceinline__ void alias_dec_group(TmaWindow& win, uint32_t& x, uint32_t ring_end, uint32_t tab_lane, uint8_t* og, uint32_t lt,
+                                                uint32_t lane, uint32_t sb_rt, uint32_t* __restrict__ status)
+{
+    using P = AliasDecShip;
+    if (win.cur >= ring_end) {
+        win.cur -= P::kRing;
+        win.limit -= P::kRing;
+    }
+    if (__any_sync(0xffffffffu, win.cur > win.limit)) tma_advance<P>(win, lane, status);
+#pragma unroll
+    for (int j = 0; j < P::kGroup; j++) alias_dec_step_p<SB>(x, win.cur, tab_lane, og + 32 * j, lt, sb_rt, true);
+}
+
+template <uint32_t SB>
+__global__ void __launch_bounds__(AliasDecShip::kWarps * 32, AliasDecShip::kMinBlocks)
+alias_decode_persist_kernel(const uint8_t* __restrict__ blob, uint64_t blob_size, const uint64_t* __restrict__ offsets, uint32_t sb_rt,
+                            const AliasDecEntry* __restrict__ g_dec, uint8_t* __restrict__ out, uint64_t n, uint32_t chunk_syms,
+                            uint32_t n_chunks, DecodeWork* __restrict__ work, uint32_t* __restrict__ status)
+{
+    using P = AliasDecShip;
+    extern __shared__ __align__(1024) uint8_t s_adec[];       // [32 KiB table][16 B][24 x (ring, mirror)]
+    uint4* s_tab = reinterpret_cast<uint4*>(s_adec);
+    for (uint32_t i = threadIdx.x; i < 256 * kAliasDecReplicas; i += blockDim.x) {
+        const AliasDecEntry e = g_dec[i / kAliasDecReplicas];
+        s_tab[i] = make_uint4(e.divider, e.alt0, e.alt1, e.adjust);
+    }
+    __syncthreads();
+
+    const uint32_t base = smem_addr_pinned(s_adec);
+    const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t tab_lane = base + (lane & (kAliasDecReplicas - 1)) * 16;
+    const uint32_t lt = lanemask_lt();
+    TmaWindow win;
+    win.ring = base + P::kWarpsOff + warp * P::kWarpStride;
+    win.seq_ready = kTmaSeqBase;
+
+    for (;;) {
+        uint32_t chunk = 0;
+        if (lane == 0) chunk = atomicAdd(&work->next_chunk, 1u);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        if (chunk >= n_chunks) break;
+        const uint64_t first = static_cast<uint64_t>(chunk) * chunk_syms;
+        const uint64_t left = n - first;
+        const uint32_t m = left < chunk_syms ? static_cast<uint32_t>(left) : chunk_syms;
+        const uint64_t off = offsets[chunk];
+        const uint64_t end = offsets[chunk + 1] & ~static_cast<uint64_t>(15);
+        const bool dir_bad = off + kHeaderBytes > end || end > blob_size || end - off > (1u << 30);   // the directory is not trusted
+        if (__shfl_sync(0xffffffffu, dir_bad ? 1u : 0u, 0)) {
+            if (lane == 0) atomicOr(status, kStatStream);
+            continue;
+        }
+        const uint32_t off_in = __shfl_sync(0xffffffffu, static_cast<uint32_t>(off % P::kUnit), 0);
+        const uint32_t len = __shfl_sync(0xffffffffu, static_cast<uint32_t>(end - off), 0);
+        const uint32_t seq0 = win.seq_ready;
+        const uint32_t pos0 = seq0 * P::kUnit + off_in;
+        win.end_pos = pos0 + len;
+        win.src = reinterpret_cast<uint64_t>(blob) + (off - off_in) - static_cast<uint64_t>(seq0) * P::kUnit + lane * 16;
+        win.cur = win.ring + (pos0 & (P::kRing - 1));
+        win.limit = win.cur - off_in - P::kNeed;
+        tma_issue<P>(win, seq0, lane);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        while (win.cur > win.limit) tma_advance<P>(win, lane, status);
+        __syncwarp();
+
+        // RansDecInit x 32 (rans_byte.h:109-122): lane k's state is the k-th little-endian u32; the mirror covers a wrap
+        uint32_t x = 0;
+#pragma unroll
+        for (int b = 3; b >= 0; b--) x = (x << 8) | lds_u8(win.cur + 4 * lane + b);
+        win.cur += kHeaderBytes;
+
+        uint8_t* o = out + first + lane;
+        const uint32_t ring_end = win.ring + P::kRing;
+        uint32_t todo = m >> 5;
+        for (; todo >= P::kGroup; todo -= P::kGroup) {
+            alias_dec_group<SB>(win, x, ring_end, tab_lane, o, lt, lane, sb_rt, status);
+            o += 32 * P::kGroup;
+        }
+        if (win.cur >= ring_end) {
+            win.cur -= P::kRing;
+            win.limit -= P::kRing;
+        }
+        if (__any_sync(0xffffffffu, win.cur > win.limit)) tma_advance<P>(win, lane, status);
+        for (; todo; todo--) {
+            alias_dec_step_p<SB>(x, win.cur, tab_lane, o, lt, sb_rt, true);
+            o += 32;
+        }
+        if (m & 31) alias_dec_step_p<SB>(x, win.cur, tab_lane, o, lt, sb_rt, lane < (m & 31));      // main_alias.cpp:399-404
+
+        const uint32_t pos = win.cur + (win.seq_ready * P::kUnit - P::kNeed - win.limit);
+        const bool bad = (pos != pos0 + len) || (x != kByteL);
+        if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(status, kStatStream);
+        const uint32_t seq_end = (win.end_pos + P::kUnit - 1) / P::kUnit;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        win.seq_ready = win.seq_ready < seq_end ? win.seq_ready + 1 : seq_end;
+        __syncwarp();
+    }
+    if (lane == 0) {
+        const uint32_t total = gridDim.x * P::kWarps;
+        if (atomicAdd(&work->warps_done, 1u) == total - 1) {
+            work->next_chunk = 0;
+            work->warps_done = 0;
+        }
+    }
+}
+
 
 // ---------------------------------------------------------------------------
 // K4: 32-way alias encode.  RansEncPutAlias (main_alias.cpp:241-250) = RansEncRenorm
@@ -457,8 +623,15 @@ inline void configure_alias_pair()
     cudaFuncSetAttribute(alias_encode_kernel<ALIAS, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          kAliasEncFixedSmem + (ALIAS ? (2u << 16) : 0u));
 }
+template <uint32_t SB>
+inline void configure_alias_persist()
+{
+    cudaFuncSetAttribute(alias_decode_persist_kernel<SB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(alias_decode_persist_kernel<SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, AliasDecShip::kSmemBytes);
+}
 inline void configure_alias_kernels()
 {
+    configure_alias_persist<0>(); configure_alias_persist<16>(); configure_alias_persist<14>(); configure_alias_persist<12>();
     configure_alias_pair<true, 0>(); configure_alias_pair<true, 16>(); configure_alias_pair<true, 14>(); configure_alias_pair<true, 12>();
     configure_alias_pair<false, 0>(); configure_alias_pair<false, 16>(); configure_alias_pair<false, 14>(); configure_alias_pair<false, 12>();
 }
@@ -492,10 +665,19 @@ inline int launch_alias_encode(cudaStream_t stream, uint32_t sms, const uint8_t*
 }
 inline uint32_t alias_fused_slots(uint32_t sms) { return sms * kAliasEncWarps * 2; }
 
+// work != nullptr: the persistent kernel (sms x 2 CTAs of 24 warps, chunk ids from the context's work counter)
 inline int launch_alias_decode(cudaStream_t stream, const uint8_t* blob, uint64_t blob_size, const uint64_t* offsets, uint32_t sb,
                                const AliasDecEntry* dec, uint8_t* out, uint64_t n, uint32_t chunk_syms, uint32_t n_chunks,
-                               uint32_t* status)
+                               uint32_t* status, DecodeWork* work = nullptr, uint32_t sms = 0)
 {
+    if (work) {
+        using P = AliasDecShip;
+        const uint32_t want = (n_chunks + P::kWarps - 1) / P::kWarps, full = sms * P::kMinBlocks;
+        const uint32_t pgrid = want < full ? want : full;
+        RB200_ALIAS_SB_DISPATCH(sb, (alias_decode_persist_kernel<SB><<<pgrid, P::kWarps * 32, P::kSmemBytes, stream>>>(
+            blob, blob_size, offsets, sb, dec, out, n, chunk_syms, n_chunks, work, status)))
+        return 0;
+    }
     const uint32_t grid = (n_chunks + kAliasDecWarps - 1) / kAliasDecWarps;
     RB200_ALIAS_SB_DISPATCH(sb, (alias_decode_kernel<true, SB><<<grid, kAliasDecWarps * 32, kAliasDecSmem, stream>>>(
         blob, blob_size, offsets, sb, dec, out, n, chunk_syms, n_chunks, status)))

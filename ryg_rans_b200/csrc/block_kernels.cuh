@@ -21,40 +21,50 @@ namespace rb200 {
 // ---------------------------------------------------------------------------
 constexpr int kHistWarps = 8;
 
+// One histogram copy per LANE, bin-major: counter (bin, lane) lives at word bin * 32 + lane, i.e. in bank `lane`.
+// The 32 lanes of a shared-memory atomic therefore never share a bank -- whatever the symbols are: uniform data no
+// longer pays the ~3.5 wavefronts of 32 random banks, skewed data no longer serialises on one hot counter (round 1's
+// per-warp copies did both and ran at 2.6 TB/s).  All warps of the CTA add into the same 32 KiB.
 __global__ void __launch_bounds__(kHistWarps * 32)
 histogram_kernel(const uint8_t* __restrict__ in, uint64_t n, unsigned long long* __restrict__ counts)
 {
-    __shared__ uint32_t s_h[kHistWarps][256];
-    for (uint32_t i = threadIdx.x; i < kHistWarps * 256; i += blockDim.x) (&s_h[0][0])[i] = 0;
+    __shared__ uint32_t s_h[256 * 32];
+    for (uint32_t i = threadIdx.x; i < 256 * 32; i += blockDim.x) s_h[i] = 0;
     __syncthreads();
-    uint32_t* h = s_h[threadIdx.x >> 5];
+    uint32_t* h = s_h + (threadIdx.x & 31);
 
     // unaligned head (< 16 bytes) and tail (< 16 bytes) go to block 0, the 16-byte body is grid-strided
     const uint64_t head = min(n, static_cast<uint64_t>((16 - (reinterpret_cast<uintptr_t>(in) & 15)) & 15));
     const uint64_t nvec = (n - head) / 16;
     const uint4* body = reinterpret_cast<const uint4*>(in + head);
     const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
-    for (uint64_t v = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < nvec; v += stride) {
-        const uint4 q = ldg_stream_u128(body + v);
+    uint64_t v = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    auto count16 = [&](const uint4& q) {
         const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            atomicAdd(&h[w[j] & 0xff], 1u);
-            atomicAdd(&h[(w[j] >> 8) & 0xff], 1u);
-            atomicAdd(&h[(w[j] >> 16) & 0xff], 1u);
-            atomicAdd(&h[w[j] >> 24], 1u);
+            atomicAdd(&h[(w[j] & 0xff) * 32], 1u);
+            atomicAdd(&h[((w[j] >> 8) & 0xff) * 32], 1u);
+            atomicAdd(&h[((w[j] >> 16) & 0xff) * 32], 1u);
+            atomicAdd(&h[(w[j] >> 24) * 32], 1u);
         }
+    };
+    for (; v + stride < nvec; v += 2 * stride) {             // two loads in flight per thread
+        const uint4 q0 = ldg_stream_u128(body + v), q1 = ldg_stream_u128(body + v + stride);
+        count16(q0);
+        count16(q1);
     }
+    if (v < nvec) count16(ldg_stream_u128(body + v));
     if (blockIdx.x == 0) {
         const uint64_t tail_lo = head + nvec * 16;
-        for (uint64_t i = threadIdx.x; i < head; i += blockDim.x) atomicAdd(&h[in[i]], 1u);
-        for (uint64_t i = tail_lo + threadIdx.x; i < n; i += blockDim.x) atomicAdd(&h[in[i]], 1u);
+        for (uint64_t i = threadIdx.x; i < head; i += blockDim.x) atomicAdd(&h[in[i] * 32u], 1u);
+        for (uint64_t i = tail_lo + threadIdx.x; i < n; i += blockDim.x) atomicAdd(&h[in[i] * 32u], 1u);
     }
     __syncthreads();
     for (uint32_t s = threadIdx.x; s < 256; s += blockDim.x) {
         unsigned long long t = 0;
 #pragma unroll
-        for (int w = 0; w < kHistWarps; w++) t += s_h[w][s];
+        for (uint32_t l = 0; l < 32; l++) t += s_h[s * 32 + ((l + s) & 31)];      // rotated: the 32 threads of a warp read 32 banks
         if (t) atomicAdd(&counts[s], t);
     }
 }
@@ -75,6 +85,65 @@ inline void launch_histogram(cudaStream_t stream, const uint8_t* d_in, uint64_t 
 // per-block model: histogram + normalize_freqs(4096), one CTA per block
 // ---------------------------------------------------------------------------
 constexpr int kModelWarps = 8;
+
+// calc_cum_freqs + normalize_freqs(4096) (main.cpp:68-129) on 256 counts in shared memory, run by ONE warp, bit-exact:
+// s_cnt = the block's histogram (sums to block_size), s_cum / s_w = 257 / 256 words of workspace; the normalised
+// frequencies end up in s_w and in dst[0..256).
+__device__ __forceinline__ void block_normalize(const uint32_t* s_cnt, uint32_t* s_cum, uint32_t* s_w, uint16_t* __restrict__ dst,
+                                                uint32_t* __restrict__ status)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    // calc_cum_freqs (main.cpp:68-73): lane l owns symbols 8l .. 8l+7
+    uint32_t run = 0, local[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { local[j] = run; run += s_cnt[8 * lane + j]; }
+    uint32_t incl = run;
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= static_cast<uint32_t>(d)) incl += v;
+    }
+    const uint32_t base = incl - run;
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);      // == block_size
+    // resample, main.cpp:83-84 (cum[0] stays 0)
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+        s_cum[8 * lane + j] = static_cast<uint32_t>((static_cast<uint64_t>(kWordSlots) * (base + local[j])) / total);
+    if (lane == 31) s_cum[256] = kWordSlots;                       // 4096 * total / total
+    __syncwarp();
+
+    // main.cpp:90-116, symbols in order.  Moving the boundaries between donor and taker by one changes exactly
+    // two widths (donor - 1, taker + 1), so the loop runs on widths; the arg-min over 256 widths is warp-wide
+    // with the key (width << 8 | symbol): lowest width first, lowest symbol on ties, as the reference's scan.
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const uint32_t t = 8 * lane + j;
+        s_w[t] = s_cum[t + 1] - s_cum[t];
+    }
+    __syncwarp();
+    bool failed = false;
+    for (uint32_t s = 0; s < 256; s++) {
+        if (s_cnt[s] == 0 || s_w[s] != 0) continue;                // warp-uniform
+        uint32_t key = 0xffffffffu;
+        const uint4 lo = *reinterpret_cast<const uint4*>(&s_w[8 * lane]);
+        const uint4 hi = *reinterpret_cast<const uint4*>(&s_w[8 * lane + 4]);
+        const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            if (w[j] > 1) key = min(key, (w[j] << 8) | (8 * lane + j));
+        key = __reduce_min_sync(0xffffffffu, key);
+        if (key == 0xffffffffu) { failed = true; break; }           // main.cpp:104
+        __syncwarp();
+        if (lane == 0) {
+            s_w[key & 0xffu] -= 1;                                  // main.cpp:107-113 in terms of widths
+            s_w[s] += 1;
+        }
+        __syncwarp();
+    }
+    if (failed && lane == 0) atomicOr(status, kStatStream);
+#pragma unroll
+    for (int j = 0; j < 8; j++) dst[8 * lane + j] = static_cast<uint16_t>(s_w[8 * lane + j]);     // main.cpp:127
+}
 
 // Shared-memory workspace of the per-block model build.
 struct BlockModelSmem {
@@ -118,59 +187,48 @@ __device__ __forceinline__ void block_model_build(const uint8_t* __restrict__ bl
         sm.cnt[s] = t;
     }
     __syncthreads();
-    if (warp == 0) {
-        // calc_cum_freqs (main.cpp:68-73): lane l owns symbols 8l .. 8l+7
-        uint32_t run = 0, local[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) { local[j] = run; run += sm.cnt[8 * lane + j]; }
-        uint32_t incl = run;
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= static_cast<uint32_t>(d)) incl += v;
-        }
-        const uint32_t base = incl - run;
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);      // == block_size
-        // resample, main.cpp:83-84 (cum[0] stays 0)
-#pragma unroll
-        for (int j = 0; j < 8; j++)
-            sm.cum[8 * lane + j] = static_cast<uint32_t>((static_cast<uint64_t>(kWordSlots) * (base + local[j])) / total);
-        if (lane == 31) sm.cum[256] = kWordSlots;                       // 4096 * total / total
-        __syncwarp();
+    if (warp == 0) block_normalize(sm.cnt, sm.cum, sm.h[0], dst, status);      // h[0] is reused for the 256 widths
+    __syncthreads();
+}
 
-        // main.cpp:90-116, symbols in order.  Moving the boundaries between donor and taker by one changes exactly
-        // two widths (donor - 1, taker + 1), so the loop runs on widths; the arg-min over 256 widths is warp-wide
-        // with the key (width << 8 | symbol): lowest width first, lowest symbol on ties, as the reference's scan.
-        uint32_t* s_w = sm.h[0];                                        // reuse: 256 widths
-        __syncwarp();
+// The same with the bank-private histogram of histogram_kernel (one copy per lane, 32 KiB at `hist`): no bank
+// conflicts and no hot-counter serialisation.  Used by the fused per-block encoder, where the 32 KiB are the (not yet
+// built) encoder table.  s_cnt / s_cum / s_w: 256 / 257 / 256 words.
+__device__ __forceinline__ void block_model_build_wide(const uint8_t* __restrict__ blk, uint32_t block_size, uint32_t* hist, uint32_t* s_cnt,
+                                                       uint32_t* s_cum, uint32_t* s_w, uint16_t* __restrict__ dst,
+                                                       uint32_t* __restrict__ status)
+{
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint32_t i = tid; i < 256 * 32; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    {   // count_freqs, main.cpp:59-66
+        uint32_t* h = hist + lane;
+        const uint32_t head = min(block_size, static_cast<uint32_t>((16 - (reinterpret_cast<uintptr_t>(blk) & 15)) & 15));
+        const uint32_t nvec = (block_size - head) / 16;
+        const uint4* body = reinterpret_cast<const uint4*>(blk + head);
+        for (uint32_t v = tid; v < nvec; v += blockDim.x) {
+            const uint4 q = ldg_stream_u128(body + v);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const uint32_t t = 8 * lane + j;
-            s_w[t] = sm.cum[t + 1] - sm.cum[t];
-        }
-        __syncwarp();
-        bool failed = false;
-        for (uint32_t s = 0; s < 256; s++) {
-            if (sm.cnt[s] == 0 || s_w[s] != 0) continue;                // warp-uniform
-            uint32_t key = 0xffffffffu;
-            const uint4 lo = *reinterpret_cast<const uint4*>(&s_w[8 * lane]);
-            const uint4 hi = *reinterpret_cast<const uint4*>(&s_w[8 * lane + 4]);
-            const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-#pragma unroll
-            for (int j = 0; j < 8; j++)
-                if (w[j] > 1) key = min(key, (w[j] << 8) | (8 * lane + j));
-            key = __reduce_min_sync(0xffffffffu, key);
-            if (key == 0xffffffffu) { failed = true; break; }           // main.cpp:104
-            __syncwarp();
-            if (lane == 0) {
-                s_w[key & 0xffu] -= 1;                                  // main.cpp:107-113 in terms of widths
-                s_w[s] += 1;
+            for (int j = 0; j < 4; j++) {
+                atomicAdd(&h[(w[j] & 0xff) * 32], 1u);
+                atomicAdd(&h[((w[j] >> 8) & 0xff) * 32], 1u);
+                atomicAdd(&h[((w[j] >> 16) & 0xff) * 32], 1u);
+                atomicAdd(&h[(w[j] >> 24) * 32], 1u);
             }
-            __syncwarp();
         }
-        if (failed && lane == 0) atomicOr(status, kStatStream);
-#pragma unroll
-        for (int j = 0; j < 8; j++) dst[8 * lane + j] = static_cast<uint16_t>(s_w[8 * lane + j]);     // main.cpp:127
+        for (uint32_t i = tid; i < head; i += blockDim.x) atomicAdd(&h[blk[i] * 32u], 1u);
+        for (uint32_t i = head + nvec * 16 + tid; i < block_size; i += blockDim.x) atomicAdd(&h[blk[i] * 32u], 1u);
     }
+    __syncthreads();
+    for (uint32_t s = tid; s < 256; s += blockDim.x) {
+        uint32_t t = 0;
+#pragma unroll
+        for (uint32_t l = 0; l < 32; l++) t += hist[s * 32 + ((l + s) & 31)];
+        s_cnt[s] = t;
+    }
+    __syncthreads();
+    if (warp == 0) block_normalize(s_cnt, s_cum, s_w, dst, status);
     __syncthreads();
 }
 
@@ -178,9 +236,11 @@ __global__ void __launch_bounds__(kModelWarps * 32)
 block_model_kernel(const uint8_t* __restrict__ in, uint32_t block_size, uint16_t* __restrict__ block_freqs,
                    uint32_t* __restrict__ status)
 {
-    __shared__ __align__(16) BlockModelSmem sm;
-    block_model_build(in + static_cast<uint64_t>(blockIdx.x) * block_size, block_size, sm,
-                      block_freqs + static_cast<uint64_t>(blockIdx.x) * 256, status);
+    __shared__ uint32_t s_hist[256 * 32];
+    __shared__ uint32_t s_cnt[256], s_cum[257];
+    __shared__ __align__(16) uint32_t s_w[256];      // block_normalize reads it 16 bytes at a time
+    block_model_build_wide(in + static_cast<uint64_t>(blockIdx.x) * block_size, block_size, s_hist, s_cnt, s_cum, s_w,
+                           block_freqs + static_cast<uint64_t>(blockIdx.x) * 256, status);
 }
 
 inline void launch_block_models(cudaStream_t stream, const uint8_t* d_in, uint32_t n_blocks, uint32_t block_size,
@@ -346,15 +406,16 @@ block_encode_kernel(const uint8_t* __restrict__ in, uint32_t block_size, const u
 // per-warp scratch slots exactly as the fused word encoder does: publish the padded size, place the chunk of the
 // PREVIOUS block once the scanner has turned the published sizes into end offsets.  The second pass over the block's
 // 64 KiB (histogram first, then encode) is served by the L2.
-template <bool BUILD>
-__global__ void __launch_bounds__(kMaxBlockWarps * 32)
+template <bool BUILD, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 5 : 1)
 block_encode_fused_kernel(const uint8_t* __restrict__ in, uint32_t n_blocks, uint32_t block_size, uint16_t* __restrict__ block_freqs,
                           uint32_t chunk_syms, uint8_t* __restrict__ scratch, uint32_t slot_bytes, uint64_t* __restrict__ look,
                           uint32_t* __restrict__ counter, uint8_t* __restrict__ blob, uint64_t blob_cap, uint64_t* __restrict__ offsets,
                           uint32_t* __restrict__ status)
 {
-    extern __shared__ __align__(1024) uint8_t s_enc[];          // [32 KiB table][warps x 1 KiB stage + ring]
-    __shared__ __align__(16) BlockModelSmem sm;
+    extern __shared__ __align__(1024) uint8_t s_enc[];          // [32 KiB: histogram copies, then the table][warps x 1 KiB stage + ring]
+    __shared__ uint32_t s_cnt[256], s_cum[257];
+    __shared__ __align__(16) uint32_t s_w[256];      // block_normalize reads it 16 bytes at a time
     __shared__ uint32_t s_flag[1];
     __shared__ uint32_t s_block;
     uint4* s_tab = reinterpret_cast<uint4*>(s_enc);
@@ -380,12 +441,12 @@ block_encode_fused_kernel(const uint8_t* __restrict__ in, uint32_t n_blocks, uin
         uint16_t* freqs = block_freqs + static_cast<uint64_t>(block) * 256;
         bool ok;
         if (BUILD) {
-            block_model_build(blk, block_size, sm, freqs, status);
-            ok = block_prefix(&sm.h[0][0], sm.cum, &s_flag[0]);      // the widths are still in shared memory
+            block_model_build_wide(blk, block_size, reinterpret_cast<uint32_t*>(s_enc), s_cnt, s_cum, s_w, freqs, status);
+            ok = block_prefix(s_w, s_cum, &s_flag[0]);                // the widths are still in shared memory
         } else {
-            ok = block_prefix(static_cast<const uint16_t*>(freqs), sm.cum, &s_flag[0]);
+            ok = block_prefix(static_cast<const uint16_t*>(freqs), s_cum, &s_flag[0]);
         }
-        const bool r32 = block_build_enc_table(sm.cum, ok, s_tab);
+        const bool r32 = block_build_enc_table(s_cum, ok, s_tab);
         if (warp < per_block) {
             const uint32_t chunk = block * per_block + warp;
             uint8_t* slot_end = slots + (parity + 1) * static_cast<uint64_t>(slot_bytes);
@@ -416,6 +477,14 @@ inline uint32_t block_threads(uint32_t block_size, uint32_t chunk_syms)
     return warps * 32;
 }
 
+template <bool BUILD, int WARPS>
+inline void configure_block_fused()
+{
+    cudaFuncSetAttribute(block_encode_fused_kernel<BUILD, WARPS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(block_encode_fused_kernel<BUILD, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         kEncTableBytes + WARPS * kEncWarpSmem);
+}
+
 inline void configure_block_kernels()
 {
     cudaFuncSetAttribute(block_decode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -423,10 +492,7 @@ inline void configure_block_kernels()
     cudaFuncSetAttribute(block_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxBlockWarps * kRingBytes);
     cudaFuncSetAttribute(block_encode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(block_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncTableBytes + kMaxBlockWarps * kEncWarpSmem);
-    cudaFuncSetAttribute(block_encode_fused_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(block_encode_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncTableBytes + kMaxBlockWarps * kEncWarpSmem);
-    cudaFuncSetAttribute(block_encode_fused_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(block_encode_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncTableBytes + kMaxBlockWarps * kEncWarpSmem);
+    configure_block_fused<true, 8>(); configure_block_fused<false, 8>(); configure_block_fused<true, 32>(); configure_block_fused<false, 32>();
 }
 
 // grid of the fused per-block encoder: CTA 0 (scanner) + as many worker CTAs as are resident at once
@@ -434,8 +500,14 @@ inline uint32_t block_fused_grid(uint32_t sms, uint32_t n_blocks, uint32_t threa
 {
     int per_sm = 0;
     const size_t smem = kEncTableBytes + (threads / 32) * kEncWarpSmem;
-    if (build) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, block_encode_fused_kernel<true>, static_cast<int>(threads), smem);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, block_encode_fused_kernel<false>, static_cast<int>(threads), smem);
+    const int t = static_cast<int>(threads);
+    if (threads <= 256) {
+        if (build) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, block_encode_fused_kernel<true, 8>, t, smem);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, block_encode_fused_kernel<false, 8>, t, smem);
+    } else {
+        if (build) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, block_encode_fused_kernel<true, 32>, t, smem);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, block_encode_fused_kernel<false, 32>, t, smem);
+    }
     if (per_sm < 1) per_sm = 1;
     uint64_t workers = static_cast<uint64_t>(sms) * per_sm - 1;       // the scanner CTA takes one slot
     if (workers > n_blocks) workers = n_blocks;
@@ -448,12 +520,15 @@ inline void launch_block_encode_fused(cudaStream_t stream, uint32_t grid, uint32
                                       uint64_t* look, uint32_t* counter, uint8_t* blob, uint64_t blob_cap, uint64_t* offsets, uint32_t* status)
 {
     const size_t smem = kEncTableBytes + (threads / 32) * kEncWarpSmem;
-    if (build)
-        block_encode_fused_kernel<true><<<grid, threads, smem, stream>>>(d_in, n_blocks, block_size, d_freqs, chunk_syms, scratch, slot, look,
-                                                                          counter, blob, blob_cap, offsets, status);
-    else
-        block_encode_fused_kernel<false><<<grid, threads, smem, stream>>>(d_in, n_blocks, block_size, d_freqs, chunk_syms, scratch, slot, look,
-                                                                           counter, blob, blob_cap, offsets, status);
+#define RB200_BLOCK_FUSED_LAUNCH(B, W)                                                                                              \
+    block_encode_fused_kernel<B, W><<<grid, threads, smem, stream>>>(d_in, n_blocks, block_size, d_freqs, chunk_syms, scratch, slot, look, \
+                                                                     counter, blob, blob_cap, offsets, status)
+    if (threads <= 256) {
+        if (build) RB200_BLOCK_FUSED_LAUNCH(true, 8); else RB200_BLOCK_FUSED_LAUNCH(false, 8);
+    } else {
+        if (build) RB200_BLOCK_FUSED_LAUNCH(true, 32); else RB200_BLOCK_FUSED_LAUNCH(false, 32);
+    }
+#undef RB200_BLOCK_FUSED_LAUNCH
 }
 
 inline void launch_block_encode(cudaStream_t stream, const uint8_t* d_in, uint32_t n_blocks, uint32_t block_size,

@@ -218,8 +218,8 @@ int build_alias_device_tables(const uint32_t freqs[256], uint32_t scale_bits, Al
     if (rc != RB200_OK) return rc;
     t.scale_bits = scale_bits;
     for (int b = 0; b < 256; b++)
-        t.dec[b] = {divider[b], slot_freqs[2 * b] | (static_cast<uint32_t>(sym_id[2 * b]) << 17),
-                    slot_freqs[2 * b + 1] | (static_cast<uint32_t>(sym_id[2 * b + 1]) << 17),
+        t.dec[b] = {divider[b], (slot_freqs[2 * b] << 8) | sym_id[2 * b],
+                    (slot_freqs[2 * b + 1] << 8) | sym_id[2 * b + 1],
                     (slot_adjust[2 * b] & 0xffffu) | (slot_adjust[2 * b + 1] << 16)};
     t.remap.resize(cum[256]);
     for (uint32_t i = 0; i < cum[256]; i++) t.remap[i] = static_cast<uint16_t>(remap[i]);

@@ -610,7 +610,8 @@ int decode_device(rb200_ctx* ctx, const rb200_model* model, const uint8_t* d_blo
         return check_launch(ctx, "byte_decode_kernel");
     }
     int rc = launch_alias_decode(ctx->stream, d_blob, blob_size, d_offsets, model->scale_bits, model->d_alias_dec, d_out, n,
-                                 chunk_syms, n_chunks, ctx->d_status);
+                                 chunk_syms, n_chunks, ctx->d_status, use_persistent_decode() ? ctx->d_work : nullptr,
+                                 static_cast<uint32_t>(ctx->sms));
     if (rc == RB200_OK) rc = check_launch(ctx, "alias_decode_kernel");
     return rc;
 }

@@ -37,8 +37,9 @@ int build_word_device_tables(const uint32_t freqs[256], WordDeviceTables& t);
 //
 // decode: ONE 16-byte entry per bucket (main_alias.cpp:55-59 fused from four gathers to one):
 //   w0 = divider[b]
-//   w1 = slot_freqs[2b]   | sym_id[2b]   << 17        (taken when xm >= divider)
-//   w2 = slot_freqs[2b+1] | sym_id[2b+1] << 17        (taken when xm <  divider)
+//   w1 = slot_freqs[2b]   << 8 | sym_id[2b]           (taken when xm >= divider; slot_freqs <= 65536: 25 bits)
+//   w2 = slot_freqs[2b+1] << 8 | sym_id[2b+1]         (taken when xm <  divider)
+//   (the symbol in the low byte is what STG.U8 stores; the frequency is one shift away)
 //   w3 = (slot_adjust[2b] & 0xffff) | (slot_adjust[2b+1] & 0xffff) << 16
 //   xm - slot_adjust is the position inside the symbol's range, < freq <= 65536, so 16 bits of
 //   the adjust are enough: bias = (xm - adjust16) & 0xffff.

@@ -82,8 +82,9 @@ constexpr int kRefillTma = 0;       // cp.async.bulk (UBLKCP) by one elected lan
 constexpr int kRefillCpAsync = 1;   // cp.async.cg 16 bytes per lane (LDGSTS), commit/wait groups
 
 template <int kWarps_, int kMinBlocks_, int kGroup_, int kRefill_ = kRefillTma, int kUnitLog_ = 9, int kWideMul_ = 0, int kTexEvery_ = 0,
-          int kAblate_ = 0, bool kIadd3_ = false>
+          int kAblate_ = 0, bool kIadd3_ = false, uint32_t kTableBytes_ = kWordSlots * 4>
 struct DecPolicy {
+    static constexpr uint32_t kTableBytes = kTableBytes_;   // decode table at the start of the CTA's shared memory
     static constexpr bool kIadd3 = kIadd3_;           // refill address / cursor update as cur + r + r (IADD3, ALU pipe) instead of IMAD
     static constexpr int kWarps = kWarps_;            // warps per CTA
     static constexpr int kMinBlocks = kMinBlocks_;    // CTAs per SM the register budget is sized for
@@ -98,7 +99,7 @@ struct DecPolicy {
     static constexpr uint32_t kMirror = (kNeed + 15u) & ~15u;             // copy of the ring's first bytes behind its end
     static constexpr uint32_t kBarsOff = kRing + kMirror;                 // per warp: [ring][mirror][kTmaUnits mbarriers]
     static constexpr uint32_t kWarpStride = kBarsOff + 8 * kTmaUnits;
-    static constexpr uint32_t kWarpsOff = kWordSlots * 4 + 16;            // [16 KiB table][table mbarrier]
+    static constexpr uint32_t kWarpsOff = kTableBytes_ + 16;              // [table][table mbarrier]
     static constexpr uint32_t kSmemBytes = kWarpsOff + kWarps_ * kWarpStride;
     static_assert(kGroup_ >= 1 && kGroup_ * 64 <= 512, "one advance per group must be enough");
     static_assert(kNeed <= (kTmaUnits - 2) * kUnit + 2, "a group must fit between the cursor's unit and the slot being refilled");
