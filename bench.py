@@ -39,7 +39,7 @@ WORKLOADS = {
     "blocks_64KiB_word32": ("blocks", 12, "blocks", "configs[4]: this GPU's 8192 of the 64 Ki blocks of 64 KiB, one model per block"),
     "uniform_1GiB_rans64": ("rans64", 14, "uniform", "the reference's CPU-baseline coder (rans64.h) on the GPU"),
 }
-DECODE_KERNEL = {"word": "word_decode_tma_kernel", "alias": "alias_decode_kernel", "blocks": "block_decode_kernel",
+DECODE_KERNEL = {"word": "word_decode_tma_kernel", "alias": "alias_decode_persist_kernel", "blocks": "block_decode_kernel",
                  "rans64": "rans64_decode_kernel"}
 BLOCK_SIZE = 65536
 
