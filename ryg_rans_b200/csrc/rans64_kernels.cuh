@@ -98,17 +98,21 @@ struct Rans64EncState {
     uint32_t flags;
 };
 
-// Rans64EncPutSymbol for 32 lanes (rans64.h:262-278); tab = 256 x 32 B {rcp_lo, rcp_hi, freq, bias, cmpl, shift, -, -}
-__device__ __forceinline__ void rans64_enc_step(Rans64EncState& st, uint32_t sym, uint32_t tab, uint32_t ring, uint32_t gt, uint32_t sb,
+// Rans64EncPutSymbol for 32 lanes (rans64.h:262-278).  tab_lane = this lane's replica of the 256-entry table
+// {rcp_lo, rcp_hi, bias, cmpl_freq | rcp_shift << 20 | bad << 31}: one 16-byte Rans64EncSymbol image per symbol (freq
+// is M - cmpl_freq), replicated 8x so that the 8 lanes of a quarter-warp hit 8 different 16-byte bank groups -- ONE
+// conflict-free LDS.128 per step.  (Round 1 read the 32-byte image with two LDS.128 from an unreplicated table: ~28
+// wavefronts per step, shared-memory data pipe 99 % busy, 3.8 ms per GiB.)
+__device__ __forceinline__ void rans64_enc_step(Rans64EncState& st, uint32_t sym, uint32_t tab_lane, uint32_t ring, uint32_t gt, uint32_t sb,
                                                 bool active)
 {
     bool need = false;
-    uint4 a = make_uint4(0, 0, 1, 0), b = make_uint4(0, 0, 0, 0);
+    uint4 e = make_uint4(0, 0, 0, 0);
     if (active) {
-        a = lds_u128_ro(tab + 32u * sym);
-        b = lds_u128_ro(tab + 32u * sym + 16);
-        st.flags |= b.y;
-        const uint64_t x_max = static_cast<uint64_t>(a.z) << (63 - sb);                // ((L >> sb) << 32) * freq, :269
+        e = lds_u128_ro(tab_lane + sym * (kEncReplicas * 16));
+        st.flags |= e.w;
+        const uint32_t freq = (1u << sb) - (e.w & 0xfffffu);
+        const uint64_t x_max = static_cast<uint64_t>(freq) << (63 - sb);               // ((L >> sb) << 32) * freq, :269
         need = st.x >= x_max;
     }
     const uint32_t mask = __ballot_sync(0xffffffffu, need);
@@ -120,9 +124,9 @@ __device__ __forceinline__ void rans64_enc_step(Rans64EncState& st, uint32_t sym
     }
     st.wpos -= 4u * __popc(mask);
     if (active) {
-        const uint64_t rcp = static_cast<uint64_t>(a.x) | (static_cast<uint64_t>(a.y) << 32);
-        const uint64_t q = __umul64hi(st.x, rcp) >> (b.y & 63u);                       // :276
-        st.x = st.x + a.w + q * b.x;                                                   // :277
+        const uint64_t rcp = static_cast<uint64_t>(e.x) | (static_cast<uint64_t>(e.y) << 32);
+        const uint64_t q = __umul64hi(st.x, rcp) >> ((e.w >> 20) & 63u);               // :276
+        st.x = st.x + e.z + q * (e.w & 0xfffffu);                                      // :277
     }
 }
 
@@ -131,9 +135,12 @@ rans64_encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_
                      const uint4* __restrict__ g_enc,      // 256 x 2 x uint4
                      uint8_t* __restrict__ scratch, uint32_t slot_bytes, uint32_t* __restrict__ sizes, uint32_t* __restrict__ status)
 {
-    extern __shared__ __align__(1024) uint8_t s_r64e[];      // [16 x 1 KiB stage + ring][8 KiB table]
+    extern __shared__ __align__(1024) uint8_t s_r64e[];      // [16 x 1 KiB stage + ring][32 KiB table, 8 replicas]
     uint4* s_tab = reinterpret_cast<uint4*>(s_r64e + kRans64Warps * kEncWarpSmem);
-    for (uint32_t i = threadIdx.x; i < 512; i += blockDim.x) s_tab[i] = g_enc[i];
+    for (uint32_t i = threadIdx.x; i < 256 * kEncReplicas; i += blockDim.x) {
+        const uint4 a = g_enc[2 * (i / kEncReplicas)], b = g_enc[2 * (i / kEncReplicas) + 1];   // {rcp_lo, rcp_hi, freq, bias}, {cmpl, shift | bad, -, -}
+        s_tab[i] = make_uint4(a.x, a.y, a.w, (b.x & 0xfffffu) | ((b.y & 63u) << 20) | (b.y & kEncBadSymbol));
+    }
     __syncthreads();
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -143,7 +150,7 @@ rans64_encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_
     const uint32_t m = static_cast<uint32_t>(min(static_cast<uint64_t>(chunk_syms), n - first));
     const uint8_t* chunk_in = in + first;
     const uint32_t wsm = smem_addr(s_r64e) + warp * kEncWarpSmem;
-    const uint32_t stage = wsm, ring = wsm + kEncStageBytes, tab = smem_addr(s_tab);
+    const uint32_t stage = wsm, ring = wsm + kEncStageBytes, tab = smem_addr(s_tab) + (lane & (kEncReplicas - 1)) * 16;
     uint8_t* slot_end = scratch + static_cast<uint64_t>(chunk + 1) * slot_bytes;
     const uint32_t gt = lanemask_gt();
 
@@ -216,6 +223,7 @@ inline void configure_rans64_kernels()
     cudaFuncSetAttribute(rans64_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRans64Warps * kRingBytes + 2048 + (1u << 16));
     cudaFuncSetAttribute(rans64_decode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(rans64_encode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(rans64_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRans64Warps * kEncWarpSmem + kEncTableBytes);
 }
 
 inline void launch_rans64_decode(cudaStream_t stream, const uint8_t* blob, uint64_t blob_size, const uint64_t* offsets, uint32_t sb,
@@ -230,7 +238,7 @@ inline void launch_rans64_encode(cudaStream_t stream, const uint8_t* d_in, uint6
                                  const uint4* enc, uint8_t* scratch, uint32_t slot, uint32_t* sizes, uint32_t* status)
 {
     const uint32_t grid = (n_chunks + kRans64Warps - 1) / kRans64Warps;
-    rans64_encode_kernel<<<grid, kRans64Warps * 32, kRans64Warps * kEncWarpSmem + 8192, stream>>>(d_in, n, chunk_syms, n_chunks, sb, enc,
+    rans64_encode_kernel<<<grid, kRans64Warps * 32, kRans64Warps * kEncWarpSmem + kEncTableBytes, stream>>>(d_in, n, chunk_syms, n_chunks, sb, enc,
                                                                                                   scratch, slot, sizes, status);
 }
 
