@@ -82,6 +82,16 @@ uint32_t meta_crc(const Header& h, const uint32_t* freqs, const uint64_t* offset
     return crc32_update(c, offsets, (h.n_chunks + 1) * sizeof(uint64_t));
 }
 
+// what rb200_model_create would accept: a known coder, its scale_bits range, frequencies that sum to 1 << scale_bits
+bool model_fields_ok(uint32_t coder, uint32_t scale_bits, const uint32_t* freqs)
+{
+    if (coder > RB200_CODER_RANS64 || scale_bits < 8 || scale_bits > 16) return false;
+    if (coder == RB200_CODER_WORD && scale_bits != 12) return false;
+    uint64_t sum = 0;
+    for (int s = 0; s < 256; s++) sum += freqs[s];
+    return sum == (1ull << scale_bits);
+}
+
 }  // namespace
 
 extern "C" size_t rb200_container_size(size_t n_chunks, size_t blob_bytes) { return blob_offset(n_chunks) + blob_bytes; }
@@ -91,6 +101,7 @@ extern "C" int rb200_container_pack(int coder, uint32_t scale_bits, uint32_t chu
                                     size_t out_cap, size_t* out_size)
 {
     if (!freqs || !offsets || (!blob && blob_bytes) || !out || !chunk_syms) return RB200_E_ARG;
+    if (coder < 0 || !model_fields_ok(static_cast<uint32_t>(coder), scale_bits, freqs)) return RB200_E_MODEL;   // never write what open rejects
     const size_t n_chunks = rb200_chunk_count(n, chunk_syms);
     if (offsets[n_chunks] != blob_bytes || (blob_bytes & 15)) return RB200_E_ARG;
     const size_t total = rb200_container_size(n_chunks, blob_bytes);
@@ -139,7 +150,9 @@ extern "C" int rb200_container_open(const uint8_t* buf, size_t size, rb200_conta
     const uint64_t* offsets = reinterpret_cast<const uint64_t*>(buf + sizeof(Header) + 256 * sizeof(uint32_t));
     if (reinterpret_cast<uintptr_t>(buf) & 7) return RB200_E_ARG;
     if (meta_crc(h, freqs, offsets) != h.meta_crc) return RB200_E_STREAM;
+    if (!model_fields_ok(h.coder, h.scale_bits, freqs)) return RB200_E_STREAM;        // CRC-valid but inconsistent
     if (offsets[h.n_chunks] != h.blob_bytes) return RB200_E_STREAM;
+    if (h.n_chunks && offsets[0] >= 16) return RB200_E_STREAM;                        // the first stream starts inside the first vector
     for (uint64_t c = 0; c < h.n_chunks; c++)
         if (offsets[c] > offsets[c + 1]) return RB200_E_STREAM;
     if ((h.flags & RB200_CONTAINER_CRC_BLOB) && crc32_update(0, buf + boff, h.blob_bytes) != h.blob_crc) return RB200_E_STREAM;

@@ -19,15 +19,20 @@ namespace rb200 {
 constexpr uint64_t kRans64L = 1ull << 31;          // RANS64_L, rans64.h:59
 constexpr uint32_t kRans64HeaderBytes = 256;       // 32 lanes x u64 (Rans64EncFlush x 32)
 constexpr int kRans64Warps = 16;
+constexpr uint32_t kRans64DecReplicas = 16;        // an LDS.64 is served 16 lanes at a time: one {start, freq} copy per lane of a half-warp
+constexpr uint32_t kRans64DecSymBytes = 256 * kRans64DecReplicas * 8;      // 32 KiB
 
-__device__ __forceinline__ void rans64_dec_step(uint64_t& x, uint32_t& cursor, uint32_t tab, uint32_t ring, uint8_t* o, uint32_t lt,
-                                                uint32_t sb, bool active)
+// tab = shared address of cum2sym[1 << sb]; syms_lane = this lane's replica of the 256 x {start, freq} table that follows it
+// (16 replicas, entry s of replica r at (s * 16 + r) * 8: the 16 lanes of each LDS.64 phase hit 16 different 8-byte bank
+// groups whatever their symbols are)
+__device__ __forceinline__ void rans64_dec_step(uint64_t& x, uint32_t& cursor, uint32_t tab, uint32_t syms_lane, uint32_t ring, uint8_t* o,
+                                                uint32_t lt, uint32_t sb, bool active)
 {
     bool need = false;
     if (active) {
         const uint32_t cf = static_cast<uint32_t>(x) & ((1u << sb) - 1);               // rans64.h:120
         const uint32_t s = lds_u8_ro(tab + cf);                                        // main64.cpp:202
-        const uint2 ds = lds_u64_ro(tab + (1u << sb) + 8u * s);                        // Rans64DecSymbol {start, freq}
+        const uint2 ds = lds_u64_ro(syms_lane + s * (kRans64DecReplicas * 8));         // Rans64DecSymbol {start, freq}
         x = static_cast<uint64_t>(ds.y) * (x >> sb) + cf - ds.x;                       // rans64.h:297
         *o = static_cast<uint8_t>(s);
         need = x < kRans64L;                                                           // :309
@@ -44,10 +49,15 @@ rans64_decode_kernel(const uint8_t* __restrict__ blob, uint64_t blob_size, const
                      const uint8_t* __restrict__ g_tab,   // cum2sym[1 << sb] + 256 x {start, freq}
                      uint8_t* __restrict__ out, uint64_t n, uint32_t chunk_syms, uint32_t n_chunks, uint32_t* __restrict__ status)
 {
-    extern __shared__ __align__(1024) uint8_t s_r64[];        // [16 x 1 KiB rings][table]
+    extern __shared__ __align__(1024) uint8_t s_r64[];        // [16 x 1 KiB rings][cum2sym][256 x 16 replicas x {start, freq}]
     uint4* s_tab = reinterpret_cast<uint4*>(s_r64 + kRans64Warps * kRingBytes);
-    const uint32_t vecs = ((1u << sb) + 2048) / 16;
+    const uint32_t vecs = (1u << sb) / 16;
     for (uint32_t i = threadIdx.x; i < vecs; i += blockDim.x) s_tab[i] = reinterpret_cast<const uint4*>(g_tab)[i];
+    {
+        const uint2* g_syms = reinterpret_cast<const uint2*>(g_tab + (1u << sb));
+        uint2* s_syms = reinterpret_cast<uint2*>(s_r64 + kRans64Warps * kRingBytes + (1u << sb));
+        for (uint32_t i = threadIdx.x; i < 256 * kRans64DecReplicas; i += blockDim.x) s_syms[i] = g_syms[i / kRans64DecReplicas];
+    }
     __syncthreads();
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -72,21 +82,22 @@ rans64_decode_kernel(const uint8_t* __restrict__ blob, uint64_t blob_size, const
 
     const uint32_t lt = lanemask_lt();
     const uint32_t tab = smem_addr(s_tab);
+    const uint32_t syms_lane = tab + (1u << sb) + (lane & (kRans64DecReplicas - 1)) * 8;
     uint8_t* o = out + first + lane;
     const uint32_t steps = m >> 5, rem = m & 31;
     uint32_t g = 0;
     for (; g + 2 <= steps; g += 2) {                            // <= 128 bytes per step: top up every 2 steps
         win.top_up(cursor, lane);
-        rans64_dec_step(x, cursor, tab, win.ring, o, lt, sb, true);
-        rans64_dec_step(x, cursor, tab, win.ring, o + 32, lt, sb, true);
+        rans64_dec_step(x, cursor, tab, syms_lane, win.ring, o, lt, sb, true);
+        rans64_dec_step(x, cursor, tab, syms_lane, win.ring, o + 32, lt, sb, true);
         o += 64;
     }
     win.top_up(cursor, lane);
     if (g < steps) {
-        rans64_dec_step(x, cursor, tab, win.ring, o, lt, sb, true);
+        rans64_dec_step(x, cursor, tab, syms_lane, win.ring, o, lt, sb, true);
         o += 32;
     }
-    if (rem) rans64_dec_step(x, cursor, tab, win.ring, o, lt, sb, lane < rem);
+    if (rem) rans64_dec_step(x, cursor, tab, syms_lane, win.ring, o, lt, sb, lane < rem);
 
     const bool bad = (cursor != static_cast<uint32_t>(end)) || (x != kRans64L);
     if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(status, kStatStream);
@@ -220,7 +231,7 @@ rans64_encode_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_
 
 inline void configure_rans64_kernels()
 {
-    cudaFuncSetAttribute(rans64_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRans64Warps * kRingBytes + 2048 + (1u << 16));
+    cudaFuncSetAttribute(rans64_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRans64Warps * kRingBytes + kRans64DecSymBytes + (1u << 16));
     cudaFuncSetAttribute(rans64_decode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(rans64_encode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(rans64_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRans64Warps * kEncWarpSmem + kEncTableBytes);
@@ -230,7 +241,7 @@ inline void launch_rans64_decode(cudaStream_t stream, const uint8_t* blob, uint6
                                  const uint8_t* table, uint8_t* out, uint64_t n, uint32_t chunk_syms, uint32_t n_chunks, uint32_t* status)
 {
     const uint32_t grid = (n_chunks + kRans64Warps - 1) / kRans64Warps;
-    rans64_decode_kernel<<<grid, kRans64Warps * 32, kRans64Warps * kRingBytes + 2048 + (1u << sb), stream>>>(
+    rans64_decode_kernel<<<grid, kRans64Warps * 32, kRans64Warps * kRingBytes + kRans64DecSymBytes + (1u << sb), stream>>>(
         blob, blob_size, offsets, sb, table, out, n, chunk_syms, n_chunks, status);
 }
 

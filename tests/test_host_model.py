@@ -198,6 +198,17 @@ def test_container_open_rejects_crafted_and_truncated_input(oracle_lib, gen):
         bad = good.copy()
         struct.pack_into("<Q", bad, dir_off + 8 * idx, val)
         assert rejected(_reseal(bad)) == -4, name
+    # CRC-valid but inconsistent models / first offsets are rejected at open, not later in model_create or the kernel
+    for name, off, fmt, val in (("freqs do not sum to 1 << scale_bits", 64 + 4 * 65, "<I", 7), ("word coder with scale_bits 14", 7, "<B", 14),
+                                ("first stream starts beyond the first vector", dir_off, "<Q", 32)):
+        bad = good.copy()
+        struct.pack_into(fmt, bad, off, val)
+        assert rejected(_reseal(bad)) == -4, name
+    # and pack refuses to write what open would reject
+    for coder, sb, f in ((256, 12, freqs), (rb.CODER_WORD, 14, freqs), (rb.CODER_ALIAS, 20, freqs), (rb.CODER_WORD, 12, freqs // 2)):
+        with pytest.raises(rb.RansError) as ei:
+            api.container_pack(coder, sb, 4096, data.size, f, offs, blob, 0)
+        assert ei.value.code == -2, (coder, sb)
     # random garbage with a valid magic never gets through either
     rng = np.random.default_rng(0)
     for _ in range(200):
