@@ -491,7 +491,7 @@ int encode_word_fused(rb200_ctx* ctx, const rb200_model* model, const uint8_t* d
 {
     const uint32_t slot = slot_bytes_for(chunk_syms);
     const uint32_t grid = fused_word_grid(ctx, n_chunks);
-    int rc = reserve(ctx, ctx->scratch, static_cast<size_t>(grid) * kEncWarps * 2 * slot + 16);  // two slots per resident warp
+    int rc = reserve(ctx, ctx->scratch, static_cast<size_t>(grid) * kEncWarps * kFusedSlots * slot + 16);  // kFusedSlots per resident warp
     if (rc == RB200_OK) rc = reserve(ctx, ctx->sizes, 16 + static_cast<size_t>(n_chunks) * sizeof(uint64_t));
     if (rc != RB200_OK) return rc;
     uint32_t* counter = static_cast<uint32_t*>(ctx->sizes.p);
@@ -511,7 +511,7 @@ int reserve_encode(rb200_ctx* ctx, const rb200_model* model, uint32_t n_chunks, 
     if (!n_chunks) return RB200_OK;
     const uint32_t slot = slot_bytes_for(chunk_syms);
     if (use_fused_encode(chunk_syms) && model->coder != RB200_CODER_RANS64) {
-        const size_t slots = model->coder == RB200_CODER_WORD ? static_cast<size_t>(fused_word_grid(ctx, n_chunks)) * kEncWarps * 2
+        const size_t slots = model->coder == RB200_CODER_WORD ? static_cast<size_t>(fused_word_grid(ctx, n_chunks)) * kEncWarps * kFusedSlots
                                                               : static_cast<size_t>(alias_fused_slots(static_cast<uint32_t>(ctx->sms)));
         int rc = reserve(ctx, ctx->scratch, slots * slot + 16);
         if (rc == RB200_OK) rc = reserve(ctx, ctx->sizes, 16 + static_cast<size_t>(n_chunks) * sizeof(uint64_t));

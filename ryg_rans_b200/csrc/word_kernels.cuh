@@ -422,6 +422,13 @@ __device__ __forceinline__ void word_encode_chunk(const uint8_t* __restrict__ ch
 #ifndef RB200_ENC_MINBLOCKS
 #define RB200_ENC_MINBLOCKS 3
 #endif
+#ifndef RB200_PLACE_BACKOFF
+#define RB200_PLACE_BACKOFF 1          // exponential back-off (128 ns .. 4 us) of the placement wait instead of a fixed 128 ns
+#endif
+#ifndef RB200_FUSED_SLOTS
+#define RB200_FUSED_SLOTS 3            // scratch slots per worker warp of the fused word encoder: a chunk is placed SLOTS - 1 chunks late (2, 3, 4 measured: 1.155 / 1.126 / 1.163 ms per GiB)
+#endif
+constexpr uint32_t kFusedSlots = RB200_FUSED_SLOTS;
 #ifndef RB200_ENC_UNIFORM_FLUSH
 #define RB200_ENC_UNIFORM_FLUSH 1      // vote on the (warp-uniform) flush test so that ptxas emits a uniform branch
 #endif
@@ -565,8 +572,12 @@ __device__ __forceinline__ void fused_place(const uint64_t* look, uint32_t chunk
                                             uint32_t produced, uint8_t* __restrict__ blob, uint64_t blob_cap,
                                             uint64_t* __restrict__ offsets, uint32_t lane, uint32_t* status)
 {
+    // Warps do not progress evenly, so the scan front (the oldest unfinished chunk) can trail this warp by a chunk time
+    // and more: the wait is real, and every poll costs ~12 issue slots that the encoding warps of the SM want.  Back off
+    // exponentially (128 ns .. 4 us): round 1 polled every 100 ns and spent a fifth of the kernel's instructions here
+    // (ncu source view: 5.3 M poll iterations per GiB, profiles/r2_encode_experiments.md).
     uint64_t v = 0;
-    uint32_t spins = 0;
+    uint32_t spins = 0, ns = 128;
     for (;;) {
         if (lane == 0) v = ld_relaxed_u64(look + chunk);
         v = __shfl_sync(0xffffffffu, v, 0);
@@ -575,7 +586,10 @@ __device__ __forceinline__ void fused_place(const uint64_t* look, uint32_t chunk
             if (lane == 0) atomicOr(status, kStatStream);
             return;
         }
-        __nanosleep(100);
+        __nanosleep(ns);
+#if RB200_PLACE_BACKOFF
+        if (ns < 4096) ns <<= 1;
+#endif
     }
     const uint64_t end = v & kLookValue;                   // E_c
     if (lane == 0) {
@@ -610,10 +624,16 @@ word_encode_fused_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t ch
         return;
     }
     const uint32_t tab = smem_addr(s_enc), wsm = tab + kEncTableBytes + warp * kEncWarpSmem;
-    uint8_t* slots = scratch + (static_cast<uint64_t>(blockIdx.x) * kEncWarps + warp) * 2 * slot_bytes;   // this warp's two slots
+    // this warp's kFusedSlots scratch slots: chunk j of this warp goes to slot j % kFusedSlots and is placed
+    // kFusedSlots - 1 chunks later
+    uint8_t* slots = scratch + (static_cast<uint64_t>(blockIdx.x) * kEncWarps + warp) * kFusedSlots * slot_bytes;
 
-    uint32_t pend_chunk = 0, pend_size = 0, parity = 0;
-    bool pending = false;
+    // The previous chunk(s) are placed late on purpose.  Warps do not progress evenly (the issue arbiter favours high warp
+    // ids), so the scan front -- the oldest unfinished chunk -- trails the fastest warps by about one chunk time: placing
+    // 32 steps into the next chunk instead was measured at 2.39 ms per GiB against 1.15 ms, 580 M polling instructions
+    // (profiles/r2_encode_experiments.md).
+    uint32_t pend_chunk[kFusedSlots - 1], pend_size[kFusedSlots - 1];      // oldest first; registers (static indexing only)
+    uint32_t n_pending = 0, cur = 0;                                        // cur = slot of the chunk being encoded
     for (;;) {
         uint32_t chunk = 0;
         if (lane == 0) chunk = atomicAdd(counter, 1u);     // chunks start in order
@@ -621,26 +641,39 @@ word_encode_fused_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t ch
         if (chunk >= n_chunks) break;
         const uint64_t first = static_cast<uint64_t>(chunk) * chunk_syms;
         const uint32_t m = static_cast<uint32_t>(min(static_cast<uint64_t>(chunk_syms), n - first));
-        uint8_t* slot_end = slots + (parity + 1) * static_cast<uint64_t>(slot_bytes);
+        uint8_t* slot_end = slots + (cur + 1) * static_cast<uint64_t>(slot_bytes);
         const uint32_t produced = word_encode_stream<R32, RB200_ENC_KEEP_HINT>(in + first, m, tab, wsm, slot_end, status);
         if (lane == 0) st_relaxed_u64(look + chunk, kLookAgg | ((produced + 15u) & ~15u));
         __syncwarp();
-        // The previous chunk is placed only now, a whole chunk later.  Warps do not progress evenly (the issue arbiter
-        // favours high warp ids), so the scan front -- the oldest unfinished chunk -- trails the fastest warps by about one
-        // chunk time: placing 32 steps into the next chunk instead was measured at 2.39 ms per GiB against 1.15 ms,
-        // 580 M polling instructions (profiles/r2_encode_experiments.md).
-        if (pending)
-            fused_place(look, pend_chunk, n_chunks, slots + (2 - parity) * static_cast<uint64_t>(slot_bytes), pend_size, blob, blob_cap,
+        if (n_pending == kFusedSlots - 1) {                // every other slot is taken: place the oldest, it sits in slot cur + 1
+            const uint32_t oldest = cur + 1 == kFusedSlots ? 0 : cur + 1;
+            fused_place(look, pend_chunk[0], n_chunks, slots + (oldest + 1) * static_cast<uint64_t>(slot_bytes), pend_size[0], blob, blob_cap,
                         offsets, lane, status);
-        pend_chunk = chunk;
-        pend_size = produced;
-        pending = true;
-        parity ^= 1;
+#pragma unroll
+            for (int j = 0; j + 1 < kFusedSlots - 1; j++) {
+                pend_chunk[j] = pend_chunk[j + 1];
+                pend_size[j] = pend_size[j + 1];
+            }
+            n_pending--;
+        }
+#pragma unroll
+        for (int j = 0; j < kFusedSlots - 1; j++)
+            if (static_cast<uint32_t>(j) == n_pending) {
+                pend_chunk[j] = chunk;
+                pend_size[j] = produced;
+            }
+        n_pending++;
+        cur = cur + 1 == kFusedSlots ? 0 : cur + 1;
         __syncwarp();
     }
-    if (pending)
-        fused_place(look, pend_chunk, n_chunks, slots + (2 - parity) * static_cast<uint64_t>(slot_bytes), pend_size, blob, blob_cap,
-                    offsets, lane, status);
+    // drain, oldest first: the k-th pending chunk sits k slots behind the next free one
+#pragma unroll
+    for (int j = 0; j < kFusedSlots - 1; j++)
+        if (static_cast<uint32_t>(j) < n_pending) {
+            const uint32_t slot = (cur + kFusedSlots - n_pending + j) % kFusedSlots;
+            fused_place(look, pend_chunk[j], n_chunks, slots + (slot + 1) * static_cast<uint64_t>(slot_bytes), pend_size[j], blob, blob_cap,
+                        offsets, lane, status);
+        }
 }
 
 // ---------------------------------------------------------------------------
