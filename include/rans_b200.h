@@ -42,6 +42,8 @@ extern "C" {
 #define RB200_E_NOMEM    -6
 #define RB200_E_SYMBOL   -7   /* encoder met a symbol whose model frequency is 0        */
 #define RB200_E_NCCL     -8   /* NCCL missing or an NCCL call failed, see rb200_last_cuda_error */
+#define RB200_E_STALL    -9   /* a bounded wait inside a kernel (8 s without progress) expired: a bug or a wedged
+                                 device, never bad input -- the kernels give up instead of hanging the GPU            */
 
 /* which memory the data pointers of a bulk call live in */
 #define RB200_MEM_HOST    0   /* host pointers; the call copies H2D/D2H and is synchronous */

@@ -9,6 +9,7 @@ namespace rb200 {
 constexpr uint32_t kStatStream = 1u;   // a chunk stream did not end where it must / bad directory
 constexpr uint32_t kStatSymbol = 2u;   // encoder saw a symbol with model frequency 0
 constexpr uint32_t kStatSpace  = 4u;   // compacted blob does not fit blob_cap
+constexpr uint32_t kStatStall  = 8u;   // a bounded wait inside a kernel expired (a bug or a wedged GPU, not bad input)
 
 constexpr uint32_t kHeaderBytes = 128; // 32 lanes x u32 final state (RansWordEncFlush / RansEncFlush x 32)
 
@@ -23,6 +24,13 @@ __device__ __forceinline__ uint32_t lanemask_gt()
     uint32_t m;
     asm("mov.u32 %0, %%lanemask_gt;" : "=r"(m));
     return m;
+}
+
+__device__ __forceinline__ uint64_t global_timer_ns()
+{
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p)

@@ -123,6 +123,7 @@ int status_to_code(uint32_t bits)
     if (bits & kStatSymbol) return RB200_E_SYMBOL;
     if (bits & kStatSpace) return RB200_E_SPACE;
     if (bits & kStatStream) return RB200_E_STREAM;
+    if (bits & kStatStall) return RB200_E_STALL;
     return RB200_OK;
 }
 
@@ -169,6 +170,7 @@ extern "C" const char* rb200_strerror(int code)
     case RB200_E_NOMEM: return "out of device memory";
     case RB200_E_SYMBOL: return "symbol with zero model frequency";
     case RB200_E_NCCL: return "NCCL error";
+    case RB200_E_STALL: return "a bounded wait inside a kernel expired";
     }
     return "unknown";
 }

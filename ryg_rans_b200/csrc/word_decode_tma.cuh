@@ -132,6 +132,9 @@ __device__ __forceinline__ void tma_issue(const TmaWindow& w, uint32_t seq, uint
     const uint32_t slot = seq & (kTmaUnits - 1);
     const uint32_t dst = w.ring + slot * P::kUnit;
     const uint64_t src = w.src + static_cast<uint64_t>(seq) * P::kUnit;
+    // The slot was last read (by other lanes too) more than a unit ago; the warp-level fence makes that ordering formal
+    // for the asynchronous writes that follow (compute-sanitizer racecheck is clean with it).
+    __syncwarp();
     if (P::kRefill == kRefillCpAsync) {
 #pragma unroll
         for (uint32_t part = 0; part < P::kUnit; part += 512) {
@@ -195,7 +198,7 @@ __device__ __forceinline__ void tma_advance(TmaWindow& w, uint32_t lane, uint32_
         asm volatile("cp.async.wait_group 1;" ::: "memory");       // everything but the unit just issued has landed
         __syncwarp();
     } else if (w.seq_ready < seq_end && !tma_wait<P>(w, w.seq_ready)) {
-        if (lane == 0) atomicOr(status, kStatStream);
+        if (lane == 0) atomicOr(status, kStatStall);
         w.end_pos = 0;                                                      // sticky: no more issues or waits
     }
     w.seq_ready++;
@@ -344,7 +347,7 @@ word_decode_tma_kernel(const uint8_t* __restrict__ blob, uint64_t blob_size, con
         uint32_t spins = 0;
         while (!mbar_try_wait(bar_tab, 0))
             if (++spins > kTmaSpinLimit) {
-                if (threadIdx.x == 0) atomicOr(status, kStatStream);
+                if (threadIdx.x == 0) atomicOr(status, kStatStall);
                 return;
             }
     }

@@ -422,9 +422,6 @@ __device__ __forceinline__ void word_encode_chunk(const uint8_t* __restrict__ ch
 #ifndef RB200_ENC_MINBLOCKS
 #define RB200_ENC_MINBLOCKS 3
 #endif
-#ifndef RB200_PLACE_BACKOFF
-#define RB200_PLACE_BACKOFF 1          // exponential back-off (128 ns .. 4 us) of the placement wait instead of a fixed 128 ns
-#endif
 #ifndef RB200_FUSED_SLOTS
 #define RB200_FUSED_SLOTS 3            // scratch slots per worker warp of the fused word encoder: a chunk is placed SLOTS - 1 chunks late (2, 3, 4 measured: 1.155 / 1.126 / 1.163 ms per GiB)
 #endif
@@ -468,7 +465,9 @@ constexpr uint32_t kEncSmemBytes = kEncTableBytes + kEncWarps * kEncWarpSmem;
 // split path because of polling)
 // ---------------------------------------------------------------------------
 constexpr uint64_t kLookAgg = 1ull << 62, kLookPrefix = 2ull << 62, kLookValue = (1ull << 62) - 1;
-constexpr uint32_t kLookSpinLimit = 1u << 22;     // a bug must not hang the GPU: give up (after ~0.5 s) and flag instead
+constexpr uint64_t kLookStallNs = 8ull * 1000 * 1000 * 1000;   // a bug must not hang the GPU: after 8 s without progress give up and
+                                                               // flag kStatStall (time, not iterations: the waits are legitimate and
+                                                               // stretch by orders of magnitude under compute-sanitizer)
 
 __device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t* p)
 {
@@ -519,8 +518,8 @@ __device__ __forceinline__ void place_stream(const uint8_t* src_end, uint32_t si
 __device__ __forceinline__ void fused_scanner(uint64_t* look, uint32_t n_chunks, uint32_t lane, uint32_t* status)
 {
     constexpr int kPer = 8;                 // consecutive entries per lane: 256 entries per trip, one warp scan per trip
-    uint64_t run = 0;
-    uint32_t pos = 0, idle = 0;
+    uint64_t run = 0, idle_since = 0;
+    uint32_t pos = 0;
     while (pos < n_chunks) {
         const uint32_t base = pos + kPer * lane;
         uint64_t v[kPer];
@@ -556,13 +555,15 @@ __device__ __forceinline__ void fused_scanner(uint64_t* look, uint32_t n_chunks,
         const uint32_t done = f == 32 ? 32u * kPer : f * kPer + r_f;
         pos += done;
         if (done == 0) {
-            if (++idle > kLookSpinLimit) {           // never hang the GPU: give up and flag
-                if (lane == 0) atomicOr(status, kStatStream);
+            const uint64_t now = global_timer_ns();
+            if (!idle_since) idle_since = now;
+            if (now - idle_since > kLookStallNs) {   // never hang the GPU: give up and flag
+                if (lane == 0) atomicOr(status, kStatStall);
                 return;
             }
             __nanosleep(100);
         } else {
-            idle = 0;
+            idle_since = 0;
         }
     }
 }
@@ -576,20 +577,22 @@ __device__ __forceinline__ void fused_place(const uint64_t* look, uint32_t chunk
     // and more: the wait is real, and every poll costs ~12 issue slots that the encoding warps of the SM want.  Back off
     // exponentially (128 ns .. 4 us): round 1 polled every 100 ns and spent a fifth of the kernel's instructions here
     // (ncu source view: 5.3 M poll iterations per GiB, profiles/r2_encode_experiments.md).
-    uint64_t v = 0;
-    uint32_t spins = 0, ns = 128;
+    uint64_t v = 0, since = 0;
+    uint32_t ns = 128;
     for (;;) {
         if (lane == 0) v = ld_relaxed_u64(look + chunk);
         v = __shfl_sync(0xffffffffu, v, 0);
         if ((v >> 62) == 2) break;
-        if (++spins > kLookSpinLimit) {
-            if (lane == 0) atomicOr(status, kStatStream);
-            return;
+        if (ns >= 4096) {                                  // only once the back-off has topped out: keep the common path short
+            const uint64_t now = global_timer_ns();
+            if (!since) since = now;
+            if (now - since > kLookStallNs) {
+                if (lane == 0) atomicOr(status, kStatStall);
+                return;
+            }
         }
         __nanosleep(ns);
-#if RB200_PLACE_BACKOFF
         if (ns < 4096) ns <<= 1;
-#endif
     }
     const uint64_t end = v & kLookValue;                   // E_c
     if (lane == 0) {
