@@ -210,6 +210,17 @@ word_decode_kernel(const uint8_t* __restrict__ blob, uint64_t blob_size, const u
 // parameters come from ONE conflict-free LDS.128: the 256-entry table is replicated 8x so
 // that the 8 lanes of a quarter-warp always hit different 16-byte bank groups.
 // ---------------------------------------------------------------------------
+// build-time switches of the encoders (A/B runs: nvcc -DNAME=value into a second .so, loaded with RB200_LIB)
+#ifndef RB200_FUSED_SLOTS
+#define RB200_FUSED_SLOTS 3            // scratch slots per worker warp of the fused word encoder: a chunk is placed SLOTS - 1 chunks late (2, 3, 4 measured: 1.155 / 1.126 / 1.163 ms per GiB)
+#endif
+constexpr uint32_t kFusedSlots = RB200_FUSED_SLOTS;
+#ifndef RB200_ENC_UNIFORM_FLUSH
+#define RB200_ENC_UNIFORM_FLUSH 1      // vote on the (warp-uniform) flush test so that ptxas emits a uniform branch
+#endif
+#ifndef RB200_ENC_KEEP_HINT
+#define RB200_ENC_KEEP_HINT false      // evict_last hint on the fused encoder's scratch stores (see word_enc_flush)
+#endif
 #ifndef RB200_ENC_ASM_RENORM
 #define RB200_ENC_ASM_RENORM 1
 #endif
@@ -421,16 +432,6 @@ __device__ __forceinline__ void word_encode_chunk(const uint8_t* __restrict__ ch
 
 #ifndef RB200_ENC_MINBLOCKS
 #define RB200_ENC_MINBLOCKS 3
-#endif
-#ifndef RB200_FUSED_SLOTS
-#define RB200_FUSED_SLOTS 3            // scratch slots per worker warp of the fused word encoder: a chunk is placed SLOTS - 1 chunks late (2, 3, 4 measured: 1.155 / 1.126 / 1.163 ms per GiB)
-#endif
-constexpr uint32_t kFusedSlots = RB200_FUSED_SLOTS;
-#ifndef RB200_ENC_UNIFORM_FLUSH
-#define RB200_ENC_UNIFORM_FLUSH 1      // vote on the (warp-uniform) flush test so that ptxas emits a uniform branch
-#endif
-#ifndef RB200_ENC_KEEP_HINT
-#define RB200_ENC_KEEP_HINT false      // evict_last hint on the fused encoder's scratch stores (see word_enc_flush)
 #endif
 template <bool R32>
 __global__ void __launch_bounds__(kEncWarps * 32, RB200_ENC_MINBLOCKS)
