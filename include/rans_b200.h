@@ -157,7 +157,8 @@ int rb200_model_from_data(rb200_ctx* ctx, int coder, uint32_t scale_bits, const 
  * [n_blocks][256] u16, normalised to 4096 per block (what RansWordTablesInitSymbol
  * would be fed, rans_word_sse41.h:64-72); the 4096-slot decode table of each block
  * is built in shared memory inside the kernel.  Each block is cut into chunks of
- * chunk_syms symbols (block_size % chunk_syms == 0); chunk index = block *
+ * chunk_syms symbols (block_size % chunk_syms == 0, and at most 32 chunks per block: one CTA per
+ * block, one warp per chunk -- RB200_E_ARG otherwise); chunk index = block *
  * (block_size / chunk_syms) + chunk-in-block; the container is the same as above. */
 int rb200_blocks_build_models(rb200_ctx* ctx, const uint8_t* in, uint32_t n_blocks, uint32_t block_size,
                               uint16_t* block_freqs, int mem_kind);
