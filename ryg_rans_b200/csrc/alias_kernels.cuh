@@ -198,80 +198,155 @@ constexpr uint32_t kAliasDecSmem = kAliasDecWarps * kRingBytes + 256 * kAliasDec
 // ---------------------------------------------------------------------------
 using AliasDecShip = DecPolicy<20, 2, 8, kRefillCpAsync, 9, 0, 0, 0, false, 256 * kAliasDecReplicas * 16>;
 
+// Experiment switches of tools/decode_lab.cu --coder alias (the shipped kernel has all of them off).  The word decoder's
+// ablation bits kAblNoSymbolStore / kAblNoRingRead / kAblNoRefill apply as they do there; two more are specific to this step:
+constexpr int kAblAliasOneByte = 16;   // ABLATION: renormalise by at most one byte (no second vote / rank / load / merge)
+// LEAN (not an ablation, bit-exact): the bucket entry is repacked when the CTA stages the table, so that the step needs
+// two selects and no byte permute, and compares the bucket-local bits of x at the TOP of a word:
+//   w0 = (own_count - 1) << (40 - SB) | own adjust,  w1 = own slot_freqs << 8 | sym,  w2 = other's,  w3 = other's adjust
+// "own" <=> x << (40 - SB) <= w0 (the low bits of w0 cannot change the outcome: the left side has zeros there); an empty
+// own part (own_count 0 wraps to all ones: always taken) carries the other slot's data.  Needs a compile-time SB > 8.
 template <uint32_t SB>
+__device__ __forceinline__ uint4 alias_lean_entry(const AliasDecEntry& e, uint32_t bucket)
+{
+    constexpr uint32_t LB = SB - 8, K = 32 - LB;
+    const uint32_t own_count = e.divider - (bucket << LB);                     // 0 .. 1 << LB (model_host.cpp: divider = lo + own)
+    const bool none = own_count == 0;
+    const uint32_t adj_own = none ? (e.adjust & 0xffffu) : (e.adjust >> 16);
+    return make_uint4(((own_count - 1u) << K) | adj_own, none ? e.alt0 : e.alt1, e.alt0, e.adjust & 0xffffu);
+}
+
+template <uint32_t SB, int ABL = 0, int LEAN = 0>
 __device__ __forceinline__ void alias_dec_step_p(uint32_t& x, uint32_t& cur, uint32_t tab_lane, uint8_t* o, uint32_t lt, uint32_t sb_rt,
                                                  bool active)
 {
     const uint32_t sb = SB ? SB : sb_rt;
     if (active) {
-        const uint32_t xm = x & ((1u << sb) - 1);                              // main_alias.cpp:258
-        const uint32_t bucket = xm >> (sb - 8);                                // :259
-        const uint4 e = lds_u128_ro(mad_u32(bucket, kAliasDecReplicas * 16, tab_lane));
-        const bool own = xm < e.x;                                             // :261 (bucket2 = 2 * bucket + 1)
-        const uint32_t fs = own ? e.z : e.y;                                   // slot_freqs << 8 | sym_id
-        const uint32_t adj = __byte_perm(e.w, 0u, own ? 0x4432u : 0x4410u);    // the taken half of the packed adjusts
-        x = mad_u32(fs >> 8, x >> sb, (xm - adj) & 0xffffu);                   // :265
-        *o = static_cast<uint8_t>(fs);                                         // :266
+        if (LEAN && SB > 8) {
+            constexpr uint32_t LB = SB > 8 ? SB - 8 : 1;
+            // bucket id: byte 1 of x by one PRMT at scale_bits 16, otherwise masked in place and scaled by the IMAD
+            const uint32_t addr = LB == 8 ? mad_u32(__byte_perm(x, 0u, 0x4441u), kAliasDecReplicas * 16, tab_lane)
+                                          : mad_u32(x & (0xffu << LB), (kAliasDecReplicas * 16) >> (LB & 7), tab_lane);
+            const uint4 e = lds_u128_ro(addr);
+            const bool own = mad_u32(x, 1u << (32 - LB), 0u) <= e.x;           // main_alias.cpp:261 on the bucket-local bits
+            const uint32_t fs = own ? e.y : e.z;
+            const uint32_t adj = own ? e.x : e.w;
+            x = mad_u32(fs >> 8, x >> SB, (x - adj) & ((1u << SB) - 1));       // :265
+            if (!(ABL & kAblNoSymbolStore)) *o = static_cast<uint8_t>(fs);     // :266
+        } else {
+            const uint32_t xm = x & ((1u << sb) - 1);                              // main_alias.cpp:258
+            const uint32_t bucket = xm >> (sb - 8);                                // :259
+            const uint4 e = lds_u128_ro(mad_u32(bucket, kAliasDecReplicas * 16, tab_lane));
+            const bool own = xm < e.x;                                             // :261 (bucket2 = 2 * bucket + 1)
+            const uint32_t fs = own ? e.z : e.y;                                   // slot_freqs << 8 | sym_id
+            const uint32_t adj = __byte_perm(e.w, 0u, own ? 0x4432u : 0x4410u);    // the taken half of the packed adjusts
+            x = mad_u32(fs >> 8, x >> sb, (xm - adj) & 0xffffu);                   // :265
+            if (!(ABL & kAblNoSymbolStore)) *o = static_cast<uint8_t>(fs);         // :266
+        }
     }
     // RansDecRenorm (rans_byte.h:307-318) for the warp: 0, 1 or 2 bytes per lane, lane k's bytes before lane k+1's,
     // most significant first.  Two predicates feed the votes, the ranked byte loads and the merges.
     const uint32_t xr = active ? x : kByteL;
     uint32_t xo = x;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p1, p2;\n\t"
-        ".reg .b32 m, r, a, b0, b1;\n\t"
-        "setp.lt.u32 p1, %2, %4;\n\t"
-        "setp.lt.u32 p2, %2, %5;\n\t"
-        "vote.sync.ballot.b32 m, p1, 0xffffffff;\n\t"
-        "and.b32 r, m, %3;\n\t"
-        "popc.b32 r, r;\n\t"
-        "add.u32 a, %1, r;\n\t"
-        "popc.b32 m, m;\n\t"
-        "add.u32 %1, %1, m;\n\t"
-        "vote.sync.ballot.b32 m, p2, 0xffffffff;\n\t"
-        "and.b32 r, m, %3;\n\t"
-        "popc.b32 r, r;\n\t"
-        "add.u32 a, a, r;\n\t"
-        "popc.b32 m, m;\n\t"
-        "add.u32 %1, %1, m;\n\t"
-        "ld.shared.u8 b0, [a];\n\t"              // unpredicated: ring + mirror make both reads safe for every lane
-        "ld.shared.u8 b1, [a+1];\n\t"
-        "@p1 mad.lo.u32 %0, %0, 256, b0;\n\t"
-        "@p2 mad.lo.u32 %0, %0, 256, b1;\n\t"
-        "}"
-        : "+r"(xo), "+r"(cur)
-        : "r"(xr), "r"(lt), "n"(kByteL), "n"(kByteL >> 8));
+    if (ABL & kAblAliasOneByte) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p1;\n\t"
+            ".reg .b32 m, r, a, b0;\n\t"
+            "setp.lt.u32 p1, %2, %4;\n\t"
+            "vote.sync.ballot.b32 m, p1, 0xffffffff;\n\t"
+            "and.b32 r, m, %3;\n\t"
+            "popc.b32 r, r;\n\t"
+            "add.u32 a, %1, r;\n\t"
+            "popc.b32 m, m;\n\t"
+            "add.u32 %1, %1, m;\n\t"
+            "ld.shared.u8 b0, [a];\n\t"
+            "@p1 mad.lo.u32 %0, %0, 256, b0;\n\t"
+            "}"
+            : "+r"(xo), "+r"(cur)
+            : "r"(xr), "r"(lt), "n"(kByteL));
+    } else if (ABL & kAblNoRingRead) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p1, p2;\n\t"
+            ".reg .b32 m, r, a, b0;\n\t"
+            "setp.lt.u32 p1, %2, %4;\n\t"
+            "setp.lt.u32 p2, %2, %5;\n\t"
+            "vote.sync.ballot.b32 m, p1, 0xffffffff;\n\t"
+            "and.b32 r, m, %3;\n\t"
+            "popc.b32 r, r;\n\t"
+            "add.u32 a, %1, r;\n\t"
+            "popc.b32 m, m;\n\t"
+            "add.u32 %1, %1, m;\n\t"
+            "vote.sync.ballot.b32 m, p2, 0xffffffff;\n\t"
+            "and.b32 r, m, %3;\n\t"
+            "popc.b32 r, r;\n\t"
+            "add.u32 a, a, r;\n\t"
+            "popc.b32 m, m;\n\t"
+            "add.u32 %1, %1, m;\n\t"
+            "and.b32 b0, a, 255;\n\t"
+            "@p1 mad.lo.u32 %0, %0, 256, b0;\n\t"
+            "@p2 mad.lo.u32 %0, %0, 256, b0;\n\t"
+            "}"
+            : "+r"(xo), "+r"(cur)
+            : "r"(xr), "r"(lt), "n"(kByteL), "n"(kByteL >> 8));
+    } else {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p1, p2;\n\t"
+            ".reg .b32 m, r, a, b0, b1;\n\t"
+            "setp.lt.u32 p1, %2, %4;\n\t"
+            "setp.lt.u32 p2, %2, %5;\n\t"
+            "vote.sync.ballot.b32 m, p1, 0xffffffff;\n\t"
+            "and.b32 r, m, %3;\n\t"
+            "popc.b32 r, r;\n\t"
+            "add.u32 a, %1, r;\n\t"
+            "popc.b32 m, m;\n\t"
+            "add.u32 %1, %1, m;\n\t"
+            "vote.sync.ballot.b32 m, p2, 0xffffffff;\n\t"
+            "and.b32 r, m, %3;\n\t"
+            "popc.b32 r, r;\n\t"
+            "add.u32 a, a, r;\n\t"
+            "popc.b32 m, m;\n\t"
+            "add.u32 %1, %1, m;\n\t"
+            "ld.shared.u8 b0, [a];\n\t"              // unpredicated: ring + mirror make both reads safe for every lane
+            "ld.shared.u8 b1, [a+1];\n\t"
+            "@p1 mad.lo.u32 %0, %0, 256, b0;\n\t"
+            "@p2 mad.lo.u32 %0, %0, 256, b1;\n\t"
+            "}"
+            : "+r"(xo), "+r"(cur)
+            : "r"(xr), "r"(lt), "n"(kByteL), "n"(kByteL >> 8));
+    }
     x = xo;
 }
 
 // kGroup steps: wrap (the mirror absorbed the previous group's overrun), fill check, steps
-template <uint32_t SB>
+template <uint32_t SB, class P, int LEAN>
 __device__ __forceinline__ void alias_dec_group(TmaWindow& win, uint32_t& x, uint32_t ring_end, uint32_t tab_lane, uint8_t* og, uint32_t lt,
                                                 uint32_t lane, uint32_t sb_rt, uint32_t* __restrict__ status)
 {
-    using P = AliasDecShip;
     if (win.cur >= ring_end) {
         win.cur -= P::kRing;
         win.limit -= P::kRing;
     }
-    if (__any_sync(0xffffffffu, win.cur > win.limit)) tma_advance<P>(win, lane, status);
+    if (!(P::kAblate & kAblNoRefill) && __any_sync(0xffffffffu, win.cur > win.limit)) tma_advance<P>(win, lane, status);
 #pragma unroll
-    for (int j = 0; j < P::kGroup; j++) alias_dec_step_p<SB>(x, win.cur, tab_lane, og + 32 * j, lt, sb_rt, true);
+    for (int j = 0; j < P::kGroup; j++) alias_dec_step_p<SB, P::kAblate, LEAN>(x, win.cur, tab_lane, og + 32 * j, lt, sb_rt, true);
 }
 
-template <uint32_t SB>
-__global__ void __launch_bounds__(AliasDecShip::kWarps * 32, AliasDecShip::kMinBlocks)
+// P, LEAN: the shipped configuration unless tools/decode_lab.cu instantiates an experiment
+template <uint32_t SB, class P = AliasDecShip, int LEAN = 0>
+__global__ void __launch_bounds__(P::kWarps * 32, P::kMinBlocks)
 alias_decode_persist_kernel(const uint8_t* __restrict__ blob, uint64_t blob_size, const uint64_t* __restrict__ offsets, uint32_t sb_rt,
                             const AliasDecEntry* __restrict__ g_dec, uint8_t* __restrict__ out, uint64_t n, uint32_t chunk_syms,
                             uint32_t n_chunks, DecodeWork* __restrict__ work, uint32_t* __restrict__ status)
 {
-    using P = AliasDecShip;
-    extern __shared__ __align__(1024) uint8_t s_adec[];       // [32 KiB table][16 B][24 x (ring, mirror)]
+    extern __shared__ __align__(1024) uint8_t s_adec[];       // [32 KiB table][16 B][kWarps x (ring, mirror)]
     uint4* s_tab = reinterpret_cast<uint4*>(s_adec);
     for (uint32_t i = threadIdx.x; i < 256 * kAliasDecReplicas; i += blockDim.x) {
         const AliasDecEntry e = g_dec[i / kAliasDecReplicas];
-        s_tab[i] = make_uint4(e.divider, e.alt0, e.alt1, e.adjust);
+        if (LEAN && SB > 8) s_tab[i] = alias_lean_entry<(SB > 8 ? SB : 9)>(e, i / kAliasDecReplicas);
+        else s_tab[i] = make_uint4(e.divider, e.alt0, e.alt1, e.adjust);
     }
     __syncthreads();
 
@@ -307,9 +382,11 @@ alias_decode_persist_kernel(const uint8_t* __restrict__ blob, uint64_t blob_size
         win.src = reinterpret_cast<uint64_t>(blob) + (off - off_in) - static_cast<uint64_t>(seq0) * P::kUnit + lane * 16;
         win.cur = win.ring + (pos0 & (P::kRing - 1));
         win.limit = win.cur - off_in - P::kNeed;
-        tma_issue<P>(win, seq0, lane);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        while (win.cur > win.limit) tma_advance<P>(win, lane, status);
+        if (!(P::kAblate & kAblNoRefill)) {
+            tma_issue<P>(win, seq0, lane);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            while (win.cur > win.limit) tma_advance<P>(win, lane, status);
+        }
         __syncwarp();
 
         // RansDecInit x 32 (rans_byte.h:109-122): lane k's state is the k-th little-endian u32; the mirror covers a wrap
@@ -322,26 +399,28 @@ alias_decode_persist_kernel(const uint8_t* __restrict__ blob, uint64_t blob_size
         const uint32_t ring_end = win.ring + P::kRing;
         uint32_t todo = m >> 5;
         for (; todo >= P::kGroup; todo -= P::kGroup) {
-            alias_dec_group<SB>(win, x, ring_end, tab_lane, o, lt, lane, sb_rt, status);
+            alias_dec_group<SB, P, LEAN>(win, x, ring_end, tab_lane, o, lt, lane, sb_rt, status);
             o += 32 * P::kGroup;
         }
         if (win.cur >= ring_end) {
             win.cur -= P::kRing;
             win.limit -= P::kRing;
         }
-        if (__any_sync(0xffffffffu, win.cur > win.limit)) tma_advance<P>(win, lane, status);
+        if (!(P::kAblate & kAblNoRefill) && __any_sync(0xffffffffu, win.cur > win.limit)) tma_advance<P>(win, lane, status);
         for (; todo; todo--) {
-            alias_dec_step_p<SB>(x, win.cur, tab_lane, o, lt, sb_rt, true);
+            alias_dec_step_p<SB, P::kAblate, LEAN>(x, win.cur, tab_lane, o, lt, sb_rt, true);
             o += 32;
         }
-        if (m & 31) alias_dec_step_p<SB>(x, win.cur, tab_lane, o, lt, sb_rt, lane < (m & 31));      // main_alias.cpp:399-404
+        if (m & 31) alias_dec_step_p<SB, P::kAblate, LEAN>(x, win.cur, tab_lane, o, lt, sb_rt, lane < (m & 31));   // main_alias.cpp:399-404
 
         const uint32_t pos = win.cur + (win.seq_ready * P::kUnit - P::kNeed - win.limit);
         const bool bad = (pos != pos0 + len) || (x != kByteL);
-        if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(status, kStatStream);
-        const uint32_t seq_end = (win.end_pos + P::kUnit - 1) / P::kUnit;
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        win.seq_ready = win.seq_ready < seq_end ? win.seq_ready + 1 : seq_end;
+        if (!P::kAblate && __any_sync(0xffffffffu, bad) && lane == 0) atomicOr(status, kStatStream);
+        if (!(P::kAblate & kAblNoRefill)) {
+            const uint32_t seq_end = (win.end_pos + P::kUnit - 1) / P::kUnit;
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            win.seq_ready = win.seq_ready < seq_end ? win.seq_ready + 1 : seq_end;
+        }
         __syncwarp();
     }
     if (lane == 0) {
@@ -623,11 +702,18 @@ inline void configure_alias_pair()
     cudaFuncSetAttribute(alias_encode_kernel<ALIAS, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          kAliasEncFixedSmem + (ALIAS ? (2u << 16) : 0u));
 }
+// Build switch: 1 ships the repacked ("lean") bucket entry of alias_dec_step_p for the compile-time scale_bits
+// (A/B in profiles/r2_alias_decode_lab.md); a runtime scale_bits always takes the plain entry.
+#ifndef RB200_ALIAS_LEAN
+#define RB200_ALIAS_LEAN 1
+#endif
+constexpr int kAliasLean = RB200_ALIAS_LEAN;
 template <uint32_t SB>
 inline void configure_alias_persist()
 {
-    cudaFuncSetAttribute(alias_decode_persist_kernel<SB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(alias_decode_persist_kernel<SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, AliasDecShip::kSmemBytes);
+    auto k = alias_decode_persist_kernel<SB, AliasDecShip, kAliasLean>;
+    cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, AliasDecShip::kSmemBytes);
 }
 inline void configure_alias_kernels()
 {
@@ -674,7 +760,7 @@ inline int launch_alias_decode(cudaStream_t stream, const uint8_t* blob, uint64_
         using P = AliasDecShip;
         const uint32_t want = (n_chunks + P::kWarps - 1) / P::kWarps, full = sms * P::kMinBlocks;
         const uint32_t pgrid = want < full ? want : full;
-        RB200_ALIAS_SB_DISPATCH(sb, (alias_decode_persist_kernel<SB><<<pgrid, P::kWarps * 32, P::kSmemBytes, stream>>>(
+        RB200_ALIAS_SB_DISPATCH(sb, (alias_decode_persist_kernel<SB, P, kAliasLean><<<pgrid, P::kWarps * 32, P::kSmemBytes, stream>>>(
             blob, blob_size, offsets, sb, dec, out, n, chunk_syms, n_chunks, work, status)))
         return 0;
     }

@@ -215,3 +215,68 @@ def test_container_open_rejects_crafted_and_truncated_input(oracle_lib, gen):
         junk = rng.integers(0, 256, int(rng.integers(64, 4096)), dtype=np.uint8)
         junk[:8] = good[:8]
         assert rejected(junk) == -4
+
+
+def _alias_step_plain(x, sb, divider, slot_adjust, slot_freqs, sym_id):
+    """RansDecGetAlias (main_alias.cpp:252-267) on the bucket entry the decode kernels stage in shared memory
+    (alias_kernels.cuh, AliasDecEntry): returns (symbol, new state before renormalisation)."""
+    xm = x & np.uint32((1 << sb) - 1)
+    b = (xm >> np.uint32(sb - 8)).astype(np.int64)
+    own = xm < divider[b]
+    fs0 = (slot_freqs[2 * b] << np.uint32(8)) | sym_id[2 * b].astype(np.uint32)
+    fs1 = (slot_freqs[2 * b + 1] << np.uint32(8)) | sym_id[2 * b + 1].astype(np.uint32)
+    fs = np.where(own, fs1, fs0)
+    adj = np.where(own, slot_adjust[2 * b + 1], slot_adjust[2 * b]) & np.uint32(0xffff)
+    rem = (xm - adj) & np.uint32(0xffff)
+    return (fs & np.uint32(0xff)), (fs >> np.uint32(8)) * (x >> np.uint32(sb)) + rem
+
+
+def _alias_step_lean(x, sb, divider, slot_adjust, slot_freqs, sym_id):
+    """The repacked entry of alias_kernels.cuh (alias_lean_entry / alias_dec_step_p<SB, ABL, LEAN = 1>): the own
+    count sits at the top of word 0 above the own adjust, the comparison is made on x << (40 - sb)."""
+    lb, k = sb - 8, 40 - sb
+    bucket = np.arange(256, dtype=np.uint32)
+    own_count = divider - (bucket << np.uint32(lb))
+    none = own_count == 0
+    adj_other = slot_adjust[0::2] & np.uint32(0xffff)
+    adj_own = np.where(none, adj_other, slot_adjust[1::2] & np.uint32(0xffff))
+    fs_other = (slot_freqs[0::2] << np.uint32(8)) | sym_id[0::2].astype(np.uint32)
+    fs_own = np.where(none, fs_other, (slot_freqs[1::2] << np.uint32(8)) | sym_id[1::2].astype(np.uint32))
+    w0 = ((own_count - np.uint32(1)) << np.uint32(k)) | adj_own
+    b = ((x >> np.uint32(lb)) & np.uint32(0xff)).astype(np.int64)
+    own = (x << np.uint32(k)) <= w0[b]
+    fs = np.where(own, fs_own[b], fs_other[b])
+    adj = np.where(own, w0[b], adj_other[b])
+    rem = (x - adj) & np.uint32((1 << sb) - 1)
+    return (fs & np.uint32(0xff)), (fs >> np.uint32(8)) * (x >> np.uint32(sb)) + rem
+
+
+@pytest.mark.parametrize("sb", [12, 14, 16])
+@pytest.mark.parametrize("kind", ["zipf", "two_symbols", "one_symbol", "uniform"])
+def test_alias_lean_entry_is_equivalent(gen, sb, kind):
+    """Every slot value x & ((1 << sb) - 1), under arbitrary upper state bits, decodes to the same symbol and the same
+    next state through the repacked bucket entry as through the plain one (the GPU A/B of the two is in
+    profiles/r2_alias_decode_lab.md; the GPU parity tests cover whichever one the library was built with)."""
+    if kind == "zipf":
+        data = gen("zipf", 50000, sb)
+    elif kind == "two_symbols":
+        data = np.concatenate([np.full(40000, 7, np.uint8), np.full(3, 250, np.uint8)])
+    elif kind == "one_symbol":
+        data = np.full(1000, 99, np.uint8)
+    else:
+        data = np.arange(1 << 16, dtype=np.uint32).astype(np.uint8)
+    st = rb.SymbolStats().count_freqs(data).normalize_freqs(1 << sb).make_alias_table()
+    rng = np.random.default_rng(sb)
+    with np.errstate(over="ignore"):
+        for _ in range(3):
+            hi = rng.integers(1 << (23 - sb), 1 << (31 - sb), size=1 << sb, dtype=np.uint32)
+            x = (hi << np.uint32(sb)) | np.arange(1 << sb, dtype=np.uint32)
+            s0, x0 = _alias_step_plain(x, sb, st.divider, st.slot_adjust, st.slot_freqs, st.sym_id)
+            s1, x1 = _alias_step_lean(x, sb, st.divider, st.slot_adjust, st.slot_freqs, st.sym_id)
+            assert np.array_equal(s0, s1) and np.array_equal(x0, x1)
+            # and both are the reference's arithmetic, main_alias.cpp:258-266, modulo 2^32
+            xm = x & np.uint32((1 << sb) - 1)
+            b2 = 2 * (xm >> np.uint32(sb - 8)).astype(np.int64)
+            b2 += xm < st.divider[b2 // 2]
+            assert np.array_equal(x0, st.slot_freqs[b2] * (x >> np.uint32(sb)) + xm - st.slot_adjust[b2])
+            assert np.array_equal(s0, st.sym_id[b2])

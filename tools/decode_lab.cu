@@ -9,7 +9,10 @@
 //
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Iinclude -Iryg_rans_b200/csrc \
 //        -o build/decode_lab tools/decode_lab.cu -Lryg_rans_b200 -lrans_b200 -Xlinker -rpath -Xlinker '$ORIGIN/../ryg_rans_b200'
-//   build/decode_lab [--n BYTES] [--chunk SYMS] [--reps K] [--dist uniform|text] [--only NAME] [--peak GBS]
+//   build/decode_lab [--n BYTES] [--chunk SYMS] [--reps K] [--dist uniform|text|zipf] [--only NAME] [--peak GBS]
+//                    [--coder word|alias]
+// --coder alias: the same for alias_decode_persist_kernel (scale_bits 16; BASELINE configs[2] is --dist zipf): the shipped
+// configuration, other occupancies, the repacked ("lean") bucket entry, and the ablations of its step.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -23,6 +26,7 @@
 
 #include "rans_b200.h"
 #include "word_decode_tma.cuh"
+#include "alias_kernels.cuh"
 
 using namespace rb200;
 
@@ -115,12 +119,171 @@ void describe(const char* name)
                 P::kSmemBytes, occ, occ * P::kWarps);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// --coder alias
+struct AliasBench {
+    const uint8_t* blob; uint64_t blob_size; const uint64_t* offsets; const AliasDecEntry* dec; uint8_t* out; uint64_t n;
+    uint32_t chunk; uint32_t n_chunks; DecodeWork* work; uint32_t* status; int sms;
+};
+struct AliasVariant {
+    std::string name;
+    bool verify;
+    std::function<void(const AliasBench&)> launch;
+    std::function<void()> describe;
+    std::string note;
+};
+template <class P, int LEAN>
+AliasVariant alias_variant(const char* name, const char* note = "")
+{
+    AliasVariant v;
+    v.name = name;
+    v.verify = P::kAblate == 0;
+    v.note = note;
+    v.launch = [](const AliasBench& b) {
+        auto k = alias_decode_persist_kernel<16, P, LEAN>;
+        static bool configured = false;
+        if (!configured) {
+            CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kSmemBytes));
+            CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            configured = true;
+        }
+        uint32_t grid = static_cast<uint32_t>(b.sms) * P::kMinBlocks;
+        const uint32_t want = (b.n_chunks + P::kWarps - 1) / P::kWarps;
+        if (grid > want) grid = want;
+        k<<<grid, P::kWarps * 32, P::kSmemBytes>>>(b.blob, b.blob_size, b.offsets, 16u, b.dec, b.out, b.n, b.chunk, b.n_chunks, b.work,
+                                                   b.status);
+    };
+    const std::string nm = name;
+    v.describe = [nm]() {
+        cudaFuncAttributes a;
+        auto k = alias_decode_persist_kernel<16, P, LEAN>;
+        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kSmemBytes));
+        CK(cudaFuncGetAttributes(&a, k));
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, P::kWarps * 32, P::kSmemBytes));
+        std::printf("{\"describe\": \"%s\", \"regs\": %d, \"smem_dyn\": %u, \"ctas_per_sm\": %d, \"warps_per_sm\": %d}\n", nm.c_str(),
+                    a.numRegs, P::kSmemBytes, occ, occ * P::kWarps);
+    };
+    return v;
+}
+
+static int run_alias(uint64_t n, uint32_t chunk, int reps, const std::string& dist, const std::string& only, double peak, int sms,
+                     const uint8_t* d_in, uint8_t* d_out)
+{
+    rb200_ctx* ctx = nullptr;
+    RB(rb200_ctx_create(&ctx, 0, nullptr));
+    rb200_model* model = nullptr;
+    uint32_t freqs[256];
+    RB(rb200_model_from_data(ctx, RB200_CODER_ALIAS, 16, d_in, n, RB200_MEM_DEVICE, freqs, &model));
+    const size_t n_chunks = rb200_chunk_count(n, chunk);
+    const size_t bound = rb200_encode_bound(n, chunk);
+    uint8_t* d_blob;
+    uint64_t* d_offsets;
+    CK(cudaMalloc(&d_blob, bound + 16));
+    CK(cudaMalloc(&d_offsets, (n_chunks + 1) * sizeof(uint64_t)));
+    RB(rb200_encode(ctx, model, d_in, n, chunk, d_blob, bound, d_offsets, nullptr, RB200_MEM_DEVICE));
+    RB(rb200_sync(ctx));
+    uint64_t blob_size = 0;
+    CK(cudaMemcpy(&blob_size, d_offsets + n_chunks, sizeof blob_size, cudaMemcpyDeviceToHost));
+
+    AliasDeviceTables* t = new AliasDeviceTables;
+    if (build_alias_device_tables(freqs, 16, *t) != 0) { std::fprintf(stderr, "alias table build failed\n"); return 2; }
+    AliasDecEntry* d_dec;
+    CK(cudaMalloc(&d_dec, sizeof t->dec));
+    CK(cudaMemcpy(d_dec, t->dec, sizeof t->dec, cudaMemcpyHostToDevice));
+    DecodeWork* d_work;
+    uint32_t* d_status;
+    unsigned long long* d_bad;
+    CK(cudaMalloc(&d_work, sizeof(DecodeWork)));
+    CK(cudaMalloc(&d_status, 4));
+    CK(cudaMalloc(&d_bad, 8));
+    CK(cudaMemset(d_work, 0, sizeof(DecodeWork)));
+
+    AliasBench b{d_blob, blob_size, d_offsets, d_dec, d_out, n, chunk, static_cast<uint32_t>(n_chunks), d_work, d_status, sms};
+    const double alg_bytes = static_cast<double>(n) + static_cast<double>(blob_size);
+    std::printf("{\"lab\": \"alias_decode\", \"n\": %llu, \"chunk\": %u, \"dist\": \"%s\", \"blob_bytes\": %llu, \"sms\": %d, \"peak_gbs\": %.1f}\n",
+                (unsigned long long)n, chunk, dist.c_str(), (unsigned long long)blob_size, sms, peak);
+
+    constexpr uint32_t kTab = 256 * kAliasDecReplicas * 16;
+    //                     warps, CTAs/SM, group, refill, log2(unit), -, -, ablate, -, table bytes
+    using Ship = AliasDecShip;                                                  // 2 x 20 warps
+    static_assert(Ship::kWarps == 20 && Ship::kMinBlocks == 2 && kAliasLean == 1, "the variant names below assume the shipped configuration");
+    using W24 = DecPolicy<24, 2, 8, kRefillCpAsync, 9, 0, 0, 0, false, kTab>;
+    using W16x3 = DecPolicy<16, 3, 8, kRefillCpAsync, 9, 0, 0, 0, false, kTab>;
+    using W32x1 = DecPolicy<32, 1, 8, kRefillCpAsync, 9, 0, 0, 0, false, kTab>;
+    using G4 = DecPolicy<20, 2, 4, kRefillCpAsync, 9, 0, 0, 0, false, kTab>;
+    using A2 = DecPolicy<20, 2, 8, kRefillCpAsync, 9, 0, 0, kAblNoSymbolStore, false, kTab>;
+    using A4 = DecPolicy<20, 2, 8, kRefillCpAsync, 9, 0, 0, kAblNoRingRead, false, kTab>;
+    using A8 = DecPolicy<20, 2, 8, kRefillCpAsync, 9, 0, 0, kAblNoRefill, false, kTab>;
+    using A16 = DecPolicy<20, 2, 8, kRefillCpAsync, 9, 0, 0, kAblAliasOneByte, false, kTab>;
+    using A14 = DecPolicy<20, 2, 8, kRefillCpAsync, 9, 0, 0, kAblNoSymbolStore | kAblNoRingRead | kAblNoRefill, false, kTab>;
+    using A26 = DecPolicy<20, 2, 8, kRefillCpAsync, 9, 0, 0, kAblNoSymbolStore | kAblNoRefill | kAblAliasOneByte, false, kTab>;
+    std::vector<AliasVariant> vs;
+    vs.push_back(alias_variant<Ship, 1>("ship", "SHIPPED: persistent, 2 x 20 warps/SM, 8x replicated 16-byte bucket entries repacked at staging (lean entry: two selects, no byte permute, compare at the top of a word), cp.async ring"));
+    vs.push_back(alias_variant<Ship, 0>("plain_entry", "the bucket entry as the host packs it {divider, alt0, alt1, adjusts}: +2 ALU-pipe, -1 FMA-pipe instructions per step (the first persistent version of round 2)"));
+    vs.push_back(alias_variant<W24, 1>("ship_w24x2", "48 warps/SM"));
+    vs.push_back(alias_variant<W24, 0>("plain_entry_w24x2", "plain entry, 48 warps/SM"));
+    vs.push_back(alias_variant<W16x3, 1>("ship_w16x3", "48 warps/SM in CTAs of 16"));
+    vs.push_back(alias_variant<W32x1, 1>("ship_w32x1", "32 warps/SM"));
+    vs.push_back(alias_variant<G4, 1>("ship_g4", "fill check / ring wrap every 4 steps"));
+    vs.push_back(alias_variant<A2, 1>("abl_no_symbol_store", "ABLATION on ship: no STG.U8"));
+    vs.push_back(alias_variant<A4, 1>("abl_no_ring_read", "ABLATION: renormalisation bytes = the address, no LDS.U8 pair"));
+    vs.push_back(alias_variant<A8, 1>("abl_no_refill", "ABLATION: no ring refills / waits (blob never read)"));
+    vs.push_back(alias_variant<A16, 1>("abl_one_byte", "ABLATION: at most one renormalisation byte per step (second vote / ranks / load / merge gone: -8 instructions)"));
+    vs.push_back(alias_variant<A14, 1>("abl_memory_side", "ABLATION: store + ring reads + refill gone: arithmetic, two votes and the bucket gather remain"));
+    vs.push_back(alias_variant<A26, 1>("abl_one_byte_no_store_no_refill"));
+    if (only.empty()) for (const AliasVariant& v : vs) v.describe();
+
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (const AliasVariant& v : vs) {
+        if (!only.empty() && only != v.name) continue;
+        CK(cudaMemset(d_out, 0xAA, n));
+        CK(cudaMemset(d_status, 0, 4));
+        CK(cudaMemset(d_work, 0, sizeof(DecodeWork)));
+        v.launch(b);
+        cudaError_t le = cudaDeviceSynchronize();
+        if (le != cudaSuccess) {
+            std::printf("{\"variant\": \"%s\", \"error\": \"%s\"}\n", v.name.c_str(), cudaGetErrorString(le));
+            return 3;
+        }
+        std::vector<float> ms(reps);
+        for (int r = 0; r < reps; r++) {
+            CK(cudaEventRecord(e0));
+            v.launch(b);
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            CK(cudaEventElapsedTime(&ms[r], e0, e1));
+        }
+        CK(cudaGetLastError());
+        uint32_t status = 0;
+        CK(cudaMemcpy(&status, d_status, 4, cudaMemcpyDeviceToHost));
+        unsigned long long bad = 0;
+        if (v.verify) {
+            CK(cudaMemset(d_bad, 0, 8));
+            compare_kernel<<<sms * 8, 256>>>(d_in, d_out, n, d_bad);
+            CK(cudaMemcpy(&bad, d_bad, 8, cudaMemcpyDeviceToHost));
+        }
+        std::sort(ms.begin(), ms.end());
+        const double med = ms[reps / 2], mn = ms[0];
+        std::printf("{\"variant\": \"%s\", \"ms_min\": %.4f, \"ms_median\": %.4f, \"gsym_s\": %.1f, \"gbs\": %.1f, \"roofline_frac\": %.4f, "
+                    "\"verified\": %s, \"mismatch_words\": %llu, \"status\": %u, \"note\": \"%s\"}\n",
+                    v.name.c_str(), mn, med, n / med * 1e-6, alg_bytes / med * 1e-6, alg_bytes / med * 1e-6 / peak,
+                    v.verify ? (bad == 0 && status == 0 ? "true" : "false") : "null", bad, status, v.note.c_str());
+        std::fflush(stdout);
+    }
+    rb200_model_destroy(model);
+    rb200_ctx_destroy(ctx);
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
     uint64_t n = 1ull << 30;
     uint32_t chunk = 8192;
     int reps = 5;
-    std::string dist = "uniform", only;
+    std::string dist = "uniform", only, coder = "word";
     double peak = 6481.8;
     for (int i = 1; i < argc; i++) {
         auto arg = [&](const char* f) { return std::strcmp(argv[i], f) == 0 && i + 1 < argc; };
@@ -130,6 +293,7 @@ int main(int argc, char** argv)
         else if (arg("--dist")) dist = argv[++i];
         else if (arg("--only")) only = argv[++i];
         else if (arg("--peak")) peak = std::atof(argv[++i]);
+        else if (arg("--coder")) coder = argv[++i];
     }
     CK(cudaSetDevice(0));
     int sms = 0;
@@ -139,6 +303,15 @@ int main(int argc, char** argv)
     std::vector<uint8_t> icdf(65536);
     if (dist == "uniform") {
         for (int i = 0; i < 65536; i++) icdf[i] = static_cast<uint8_t>(i >> 8);
+    } else if (dist == "zipf") {      // Zipf(1.1) over all 256 byte values (BASELINE configs[2])
+        std::vector<double> p(256);
+        double tot = 0;
+        for (int s = 0; s < 256; s++) { p[s] = std::pow(1.0 + s, -1.1); tot += p[s]; }
+        double acc = 0; int s = 0;
+        for (int i = 0; i < 65536; i++) {
+            while (s < 255 && (acc + p[s]) / tot * 65536.0 <= i) acc += p[s++];
+            icdf[i] = static_cast<uint8_t>(s);
+        }
     } else {      // "text": Zipf(1.0) over 96 symbols, about 5 bits per symbol
         std::vector<double> p(256, 0.0);
         double tot = 0;
@@ -156,6 +329,7 @@ int main(int argc, char** argv)
     CK(cudaMalloc(&d_out, n + 16));
     gen_kernel<<<sms * 8, 256>>>(d_in, n, d_icdf, 0x1234);
     CK(cudaDeviceSynchronize());
+    if (coder == "alias") return run_alias(n, chunk, reps, dist, only, peak, sms, d_in, d_out);
 
     // ---- container from the product library
     rb200_ctx* ctx = nullptr;
