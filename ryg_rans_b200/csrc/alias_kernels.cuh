@@ -190,11 +190,11 @@ alias_decode_kernel(const uint8_t* __restrict__ blob, uint64_t blob_size, const 
 constexpr uint32_t kAliasDecSmem = kAliasDecWarps * kRingBytes + 256 * kAliasDecReplicas * 16;   // 48 KiB
 
 // ---------------------------------------------------------------------------
-// K3p: the alias decoder on the persistent plumbing of word_decode_tma.cuh -- 2 CTAs of 24 warps per SM stay resident
+// K3p: the alias decoder on the persistent plumbing of word_decode_tma.cuh -- 2 CTAs of 20 warps per SM stay resident
 // and pull chunk ids from the context's atomic counter; the 32 KiB replicated bucket table is built once per CTA; the
 // per-warp stream window is the cp.async ring with a mirror behind it, wrapped once per 8 steps, so the two ranked byte
 // reads of RansDecRenorm need no address masking (round 1's kernel spends 5 of its ~20 ALU-pipe instructions per step
-// on that, and the ALU pipe is what binds it: 85 % busy, profiles/r2_ncu_summary.md).
+// on that, and the ALU pipe is what binds it: 85 % busy).  Experiments and ablations: profiles/r2_alias_decode_lab.md.
 // ---------------------------------------------------------------------------
 using AliasDecShip = DecPolicy<20, 2, 8, kRefillCpAsync, 9, 0, 0, 0, false, 256 * kAliasDecReplicas * 16>;
 
@@ -751,7 +751,7 @@ inline int launch_alias_encode(cudaStream_t stream, uint32_t sms, const uint8_t*
 }
 inline uint32_t alias_fused_slots(uint32_t sms) { return sms * kAliasEncWarps * 2; }
 
-// work != nullptr: the persistent kernel (sms x 2 CTAs of 24 warps, chunk ids from the context's work counter)
+// work != nullptr: the persistent kernel (sms x 2 CTAs of 20 warps, chunk ids from the context's work counter)
 inline int launch_alias_decode(cudaStream_t stream, const uint8_t* blob, uint64_t blob_size, const uint64_t* offsets, uint32_t sb,
                                const AliasDecEntry* dec, uint8_t* out, uint64_t n, uint32_t chunk_syms, uint32_t n_chunks,
                                uint32_t* status, DecodeWork* work = nullptr, uint32_t sms = 0)
